@@ -1,0 +1,88 @@
+"""Shared helpers for the parity tests: rebuild the seed-derived inputs a golden
+fixture was generated from (tests/golden/make_golden.py) and compare compactly
+stored tensors."""
+import json
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from a2c_b200 import synth
+from oracle import a2c_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SAMPLE = 4096
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name), allow_pickle=False))
+
+
+def hyps_of(g):
+    return json.loads(str(g["hyps_json"]))
+
+
+def compact(a):
+    """Same compaction as make_golden._compact."""
+    a = np.asarray(a, dtype=np.float32).reshape(-1)
+    if a.size <= SAMPLE:
+        return a.copy()
+    stride = a.size // SAMPLE
+    return np.concatenate([[np.float32(np.sqrt((a.astype(np.float64) ** 2).sum()))],
+                           a[::stride][:SAMPLE]]).astype(np.float32)
+
+
+def rel_err(a, b):
+    """max |a-b| / max |b| (0 when both are all-zero)."""
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    den = np.abs(b).max() if b.size else 0.0
+    if den == 0:
+        return float(np.abs(a).max()) if a.size else 0.0
+    return float(np.abs(a - b).max() / den)
+
+
+def params_for(model, fs, h, A=3):
+    shapes = O.param_shapes(model, fs=fs, h=h, A=A)
+    return OrderedDict((k, torch.from_numpy(v)) for k, v in
+                       synth.hashed_state_dict(shapes).items())
+
+
+def small_trajectories(g, R, T):
+    seed = int(g["seed"])
+    return [synth.make_trajectory(R, T, seed=seed + 17 * k, first_rollout=(k == 0))
+            for k in range(int(g["n_updates"]))]
+
+
+def chain_frames(trajs):
+    """Frames / reset flags of consecutive rollouts as the runner sees them:
+    frame 0 of rollout k>0 is the bookmark, i.e. frame T of rollout k-1."""
+    frames = [trajs[0]["frames"]]
+    reset = [trajs[0]["reset"]]
+    for t in trajs[1:]:
+        frames.append(t["frames"][:, 1:])
+        reset.append(t["reset"][:, 1:])
+    return np.concatenate(frames, axis=1), np.concatenate(reset, axis=1)
+
+
+def golden_states(g, k, N, fs):
+    bits = np.unpackbits(g["u%d_states_bits" % k])[:N * fs * 6400]
+    return bits.reshape(N, fs, 80, 80).astype(np.uint8)
+
+
+def full_inputs(model, R, T, fs, h, seed):
+    """Mirror of make_golden.full_inputs with the oracle's prep (bit-exact)."""
+    traj = synth.make_trajectory(R, T, seed=seed)
+    states = O.prep_and_stack(traj["frames"][:, :T], traj["reset"][:, :T], fs)
+    N = R * T
+    done = ((traj["reset"][:, 1:] != 0) | (traj["rewards"] != 0)).astype(np.float32)
+    r2, d2, deltas = O.rollout_bookkeeping(traj["rewards"], done, traj["values"], 0.99)
+    rng = np.random.default_rng(seed + 1)
+    actions = torch.from_numpy(rng.integers(0, 3, size=N)).long()
+    shared = {"states_u8": torch.from_numpy(states.reshape(N, fs, 80, 80)),
+              "rewards": r2.reshape(-1).clone(), "dones": d2.reshape(-1).clone(),
+              "deltas": deltas.reshape(-1).clone(), "actions": actions}
+    if model == "GRUModel":
+        shared["h_states"] = torch.from_numpy(synth.hashed_tensor((N, h), 999, 0.5)).float()
+    return traj, shared
