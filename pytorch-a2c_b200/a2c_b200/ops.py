@@ -1,0 +1,463 @@
+"""Host-side wrappers over the C ABI: buffer management (torch tensors are only
+device memory + streams here) and the autograd glue that lets the models run
+under ``loss.backward()`` like the reference's nn.Modules do.
+
+Every function launches kernels of liba2c_b200.so on the current CUDA stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ConvShape, LossCfg, OptimCfg, StateView, call, ptr, require_cuda, stream_ptr
+
+PLANE = 6400
+
+# 0 = fp32 FFMA (exact-parity path), 1 = 3xTF32 tcgen05, 2 = bf16 tcgen05 (stated tolerance)
+_PRECISION = 0
+
+
+def set_precision(p):
+    global _PRECISION
+    if p not in (0, 1, 2):
+        raise ValueError("precision must be 0 (fp32), 1 (3xTF32) or 2 (bf16)")
+    _PRECISION = p
+
+
+def get_precision():
+    return _PRECISION
+
+
+_WS = {}
+
+
+def workspace(device, nbytes=64 << 20):
+    """Per-device scratch for split-K / conv weight-gradient partials."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    w = _WS.get(key)
+    if w is None or w.numel() < nbytes:
+        w = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _WS[key] = w
+    return w
+
+
+# --------------------------------------------------------------------------
+# stage 1
+# --------------------------------------------------------------------------
+
+class View:
+    """Python handle of an a2c_state_view; keeps the backing tensors alive."""
+
+    def __init__(self, base, fs, T, R, stride_r, stride_t, stride_c, pflag=None, pflag_stride_r=0):
+        require_cuda(base, pflag)
+        assert base.dtype in (torch.uint8, torch.float32)
+        self.base, self.pflag = base, pflag
+        self.fs, self.T, self.R = fs, T, R
+        self.N = R * T
+        self.c = StateView(base.data_ptr(), 0 if base.dtype == torch.uint8 else 1, fs, T, 0,
+                           stride_r, stride_t, stride_c,
+                           pflag.data_ptr() if pflag is not None else None, pflag_stride_r)
+
+    @property
+    def device(self):
+        return self.base.device
+
+    @staticmethod
+    def of_states(states):
+        """(N, fs, 80, 80) contiguous u8 / f32 tensor -> view with T = 1."""
+        assert states.dim() == 4 and states.shape[2:] == (80, 80) and states.is_contiguous()
+        N, fs = states.shape[:2]
+        return View(states, fs, 1, N, fs * PLANE, fs * PLANE, PLANE)
+
+    def materialize(self, dtype=torch.float32):
+        out = torch.empty((self.N, self.fs, 80, 80), dtype=dtype, device=self.device)
+        call("a2c_states_materialize", C.byref(self.c), ptr(out),
+             0 if dtype == torch.uint8 else 1, self.R, stream_ptr())
+        return out
+
+
+class PlaneRing:
+    """HBM plane ring of stage 1: planes u8 [R, T+fs, 6400] + reset flags.
+
+    State t of slot r is planes[r, t : t+fs]; ``push_frames`` preps raw frames
+    into it (a2c/preprocessing.py:11-17 + a2c/utils.py:26-43), ``carry`` makes
+    the last state the first of the next rollout (a2c/runner.py:246)."""
+
+    def __init__(self, R, T, fs, device):
+        self.R, self.T, self.fs = R, T, fs
+        self.P = T + fs
+        self.planes = torch.zeros((R, self.P, PLANE), dtype=torch.uint8, device=device)
+        self.pflag = torch.zeros((R, self.P), dtype=torch.uint8, device=device)
+        self.started = False
+
+    def push_frames(self, frames, reset, first_frame_index=0, variant=0):
+        """frames u8 [R, F, 210, 160, 3], reset u8 [R, F]; frame f lands at
+        trajectory index first_frame_index + f.  Device or pinned-host inputs."""
+        R, F = frames.shape[:2]
+        assert R == self.R and frames.shape[2:] == (210, 160, 3) and frames.dtype == torch.uint8
+        assert reset.shape == (R, F) and reset.dtype == torch.uint8
+        assert frames.is_contiguous() and reset.is_contiguous()
+        j0 = self.fs - 1 + first_frame_index
+        if frames.is_cuda:
+            require_cuda(reset)
+            call("a2c_obs_prep_stack", ptr(frames), ptr(reset), ptr(self.planes), ptr(self.pflag),
+                 R, F, self.P, j0, variant, stream_ptr())
+        else:
+            if not (frames.is_pinned() and reset.is_pinned()):
+                raise _lib.A2CError("host frames / reset must be pinned (tensor.pin_memory())")
+            call("a2c_obs_prep_stack_host", ptr(frames), ptr(reset), ptr(self.planes),
+                 ptr(self.pflag), R, F, self.P, j0, stream_ptr())
+        self.started = True
+
+    def carry(self):
+        call("a2c_ring_carry", ptr(self.planes), ptr(self.pflag), self.R, self.P, self.fs,
+             stream_ptr())
+
+    def view(self, T=None, t0=0):
+        """States t0 .. t0+T-1 of every slot (default: the T rollout states)."""
+        T = self.T if T is None else T
+        base = self.planes.view(-1)[t0 * PLANE:]
+        pf = self.pflag.view(-1)[t0:]
+        return View(base, self.fs, T, self.R, self.P * PLANE, PLANE, PLANE, pf, self.P)
+
+    def state_at(self, t):
+        """View of the single state index t of every slot (e.g. t = T: bootstrap state)."""
+        return self.view(T=1, t0=t)
+
+
+# --------------------------------------------------------------------------
+# acting / stage 2 / stage 3
+# --------------------------------------------------------------------------
+
+def sample_action(x, u, is_prob=False):
+    require_cuda(x, u)
+    x = x.contiguous().float()
+    u = u.contiguous().float()
+    B, A = x.shape
+    out = torch.empty(B, dtype=torch.int64, device=x.device)
+    call("a2c_sample_action", ptr(x), ptr(u), ptr(out), B, A, 1 if is_prob else 0, stream_ptr())
+    return out
+
+
+def delta_scan(rewards, dones, values, gamma, lambda_, want_stats=True):
+    """In-place post-rollout fix-up of rewards/dones + deltas, advs, returns.
+    rewards, dones f32 [R*T] (or [R, T]); values f32 [R, T+1]."""
+    require_cuda(rewards, dones, values)
+    R, T1 = values.shape
+    T = T1 - 1
+    assert rewards.numel() == R * T and dones.numel() == R * T
+    assert rewards.is_contiguous() and dones.is_contiguous() and values.is_contiguous()
+    dev = rewards.device
+    deltas = torch.empty(R * T, dtype=torch.float32, device=dev)
+    advs = torch.empty_like(deltas)
+    rets = torch.empty_like(deltas)
+    stats = torch.zeros(4, dtype=torch.float64, device=dev) if want_stats else None
+    call("a2c_delta_scan", ptr(rewards), ptr(dones), ptr(values), ptr(deltas), ptr(advs), ptr(rets),
+         ptr(stats), R, T, float(gamma), float(gamma * lambda_), stream_ptr())
+    return deltas, advs, rets, stats
+
+
+def discount(array, dones, factor, stats=None):
+    require_cuda(array, dones)
+    a = array.reshape(-1).contiguous().float()
+    d = dones.reshape(-1).contiguous().float()
+    out = torch.empty_like(a)
+    call("a2c_discount", ptr(a), ptr(d), ptr(out), ptr(stats), a.numel(), float(factor),
+         stream_ptr())
+    return out
+
+
+def loss_fwd_bwd(logits, vals, actions, advs, returns, adv_stats, hyps, n_global=None,
+                 ret_norm=None):
+    require_cuda(logits, vals, actions, advs)
+    N, A = logits.shape
+    logits = logits.contiguous()
+    vals = vals.reshape(-1).contiguous()
+    actions = actions.reshape(-1).contiguous()
+    assert actions.dtype == torch.int64
+    cfg = LossCfg(float(hyps["pi_coef"]), float(hyps["val_coef"]), float(hyps["entr_coef"]),
+                  1 if hyps["norm_advs"] else 0, 1 if hyps["use_nstep_rets"] else 0,
+                  int(n_global if n_global is not None else N))
+    dlogits = torch.empty_like(logits)
+    dvals = torch.empty_like(vals)
+    out = torch.empty(4, dtype=torch.float32, device=logits.device)
+    call("a2c_loss_fwd_bwd", ptr(logits), ptr(vals), ptr(actions), ptr(advs), ptr(returns),
+         ptr(adv_stats), ptr(ret_norm), C.byref(cfg), ptr(dlogits), ptr(dvals), ptr(out), N, A,
+         stream_ptr())
+    return dlogits, dvals, out
+
+
+# --------------------------------------------------------------------------
+# stage 4 primitives
+# --------------------------------------------------------------------------
+
+def gemm(A, sam, sak, B, sbk, sbn, M, N, K, out=None, ldc=None, bias=None, relu=False, beta=0,
+         precision=None, c_offset=0):
+    """out[M, N] (+)= A * B with explicit element strides (see a2c_gemm)."""
+    dev = A.device
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+        ldc = N
+    ws = workspace(dev)
+    cptr = C.c_void_p(out.data_ptr() + 4 * c_offset)
+    call("a2c_gemm", ptr(A), sam, sak, ptr(B), sbk, sbn, cptr, ldc, ptr(bias), M, N, K,
+         1 if relu else 0, beta, _PRECISION if precision is None else precision, ptr(ws),
+         ws.numel(), stream_ptr())
+    return out
+
+
+def colsum(X, M, N):
+    out = torch.empty(N, dtype=torch.float32, device=X.device)
+    call("a2c_colsum", ptr(X), ptr(out), M, N, stream_ptr())
+    return out
+
+
+def relu_bwd(dY, Y):
+    dX = torch.empty_like(dY)
+    call("a2c_relu_bwd", ptr(dY), ptr(Y), ptr(dX), dY.numel(), stream_ptr())
+    return dX
+
+
+class LinearFn(torch.autograd.Function):
+    """y = relu?(x W^T + b); x [M, K], W [N, K] (nn.Linear layout)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, relu):
+        require_cuda(x, W, b)
+        x = x.contiguous()
+        M, K = x.shape
+        N = W.shape[0]
+        y = gemm(x, K, 1, W, 1, K, M, N, K, bias=b, relu=relu)
+        ctx.save_for_backward(x, W, y if relu else None)
+        ctx.relu = relu
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = relu_bwd(dy, y)
+        M, K = x.shape
+        N = W.shape[0]
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy, N, 1, W, K, 1, M, K, N)            # dy [M,N] * W [N,K]
+        if ctx.needs_input_grad[1]:
+            dW = gemm(dy, 1, N, x, K, 1, N, K, M)            # dy^T [N,M] * x [M,K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy, M, N)
+        return dx, dW, db, None
+
+
+class LinearStateFn(torch.autograd.Function):
+    """First-layer linear reading a state view (u8 ring or f32 states)."""
+
+    @staticmethod
+    def forward(ctx, view, W, b, relu):
+        require_cuda(W, b)
+        N = W.shape[0]
+        assert W.shape[1] == view.fs * PLANE and W.is_contiguous()
+        y = torch.empty((view.N, N), dtype=torch.float32, device=W.device)
+        call("a2c_linear_state_fwd", C.byref(view.c), ptr(W), ptr(b), ptr(y), view.R, N,
+             1 if relu else 0, stream_ptr())
+        ctx.view = view
+        ctx.save_for_backward(W, y if relu else None)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        W, y = ctx.saved_tensors
+        view = ctx.view
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = relu_bwd(dy, y)
+        N = W.shape[0]
+        dW = db = None
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty_like(W)
+            ws = workspace(W.device)
+            call("a2c_linear_state_wgrad", C.byref(view.c), ptr(dy), ptr(dW), view.R, N, ptr(ws),
+                 ws.numel(), stream_ptr())
+        if ctx.needs_input_grad[2]:
+            db = colsum(dy, view.N, N)
+        return None, dW, db, None
+
+
+def conv_shape(Cin, Cout, H, W, K, stride, pad):
+    OH = (H - K + 2 * pad) // stride + 1
+    OW = (W - K + 2 * pad) // stride + 1
+    return ConvShape(Cin, Cout, H, W, OH, OW, K, stride, pad)
+
+
+class Conv2dFn(torch.autograd.Function):
+    """y = relu?(conv2d(x, W) + b), NCHW fp32.  x is a tensor or a View (first layer)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, stride, pad, relu):
+        require_cuda(W, b)
+        Cout, Cin, K, _ = W.shape
+        is_view = isinstance(x, View)
+        if is_view:
+            N, H, Wd = x.N, 80, 80
+            assert x.fs == Cin
+        else:
+            require_cuda(x)
+            x = x.contiguous()
+            N, _, H, Wd = x.shape
+        s = conv_shape(Cin, Cout, H, Wd, K, stride, pad)
+        y = torch.empty((N, Cout, s.OH, s.OW), dtype=torch.float32, device=W.device)
+        call("a2c_conv2d_fwd", None if is_view else ptr(x), C.byref(x.c) if is_view else None,
+             ptr(W), ptr(b), ptr(y), N, C.byref(s), 1 if relu else 0, stream_ptr())
+        ctx.shape, ctx.relu, ctx.is_view, ctx.N = s, relu, is_view, N
+        if is_view:
+            ctx.view = x
+            ctx.save_for_backward(W, y)
+        else:
+            ctx.save_for_backward(W, y, x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s, N = ctx.shape, ctx.N
+        if ctx.is_view:
+            W, y = ctx.saved_tensors
+            x = None
+        else:
+            W, y, x = ctx.saved_tensors
+        dy = dy.contiguous()
+        mask = y if ctx.relu else None
+        dx = dW = db = None
+        if not ctx.is_view and ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("a2c_conv2d_bwd_data", ptr(dy), ptr(mask), ptr(W), ptr(dx), N, C.byref(s),
+                 stream_ptr())
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dW = torch.empty_like(W)
+            db = torch.empty(s.Cout, dtype=torch.float32, device=W.device)
+            need = call("a2c_conv2d_bwd_weight_workspace", C.byref(s))
+            ws = workspace(W.device, max(need, 64 << 20))
+            call("a2c_conv2d_bwd_weight", ptr(x), C.byref(ctx.view.c) if ctx.is_view else None,
+                 ptr(dy), ptr(mask), ptr(dW), ptr(db), N, C.byref(s), ptr(ws), ws.numel(),
+                 stream_ptr())
+        return dx, dW, db, None, None, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta):
+        require_cuda(x, gamma, beta)
+        x = x.contiguous()
+        rows, H = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        call("a2c_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(mean), ptr(rstd), rows,
+             H, stream_ptr())
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        rows, H = x.shape
+        dx = torch.empty_like(x)
+        dg = torch.empty_like(gamma)
+        db = torch.empty_like(gamma)
+        call("a2c_layernorm_bwd", ptr(dy), ptr(x), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dg),
+             ptr(db), rows, H, stream_ptr())
+        return dx, dg, db
+
+
+class GRUCellFn(torch.autograd.Function):
+    """The reference's hand-rolled GRU (a2c/models.py:465-476):
+         z = sig(x Wx0 + h Wh0 + b0);  r = sig(x Wx1 + h Wh1 + b1)
+         h' = z*h + (1-z)*tanh(x Wx2 + (r*h) Wh2 + b2)
+    Returns (h', h'*keep) -- the second output is the masked carry of
+    a2c/updater.py:164 (keep = 1 - done, or None)."""
+
+    @staticmethod
+    def forward(ctx, x, h, Wx, Wh, b, keep):
+        require_cuda(x, h, Wx, Wh, b, keep)
+        x, h = x.contiguous(), h.contiguous()
+        B, H = h.shape
+        X = x.shape[1]
+        dev = x.device
+        gx = torch.empty((B, 3 * H), dtype=torch.float32, device=dev)
+        gh = torch.empty((B, 2 * H), dtype=torch.float32, device=dev)
+        bflat = b.reshape(3, H)
+        for g in range(3):      # x.mm(W_x[g]) + b[g]   (W_x[g] is [X, H]: right-multiply)
+            gemm(x, X, 1, Wx[g], H, 1, B, H, X, out=gx, ldc=3 * H, bias=bflat[g], c_offset=g * H)
+        for g in range(2):
+            gemm(h, H, 1, Wh[g], H, 1, B, H, H, out=gh, ldc=2 * H, c_offset=g * H)
+        z = torch.empty((B, H), dtype=torch.float32, device=dev)
+        r, rh = torch.empty_like(z), torch.empty_like(z)
+        call("a2c_gru_gates1", ptr(gx), ptr(gh), ptr(h), ptr(z), ptr(r), ptr(rh), B, H, stream_ptr())
+        gc = gemm(rh, H, 1, Wh[2], H, 1, B, H, H)
+        cand, hnew = torch.empty_like(z), torch.empty_like(z)
+        hnext = torch.empty_like(z)
+        call("a2c_gru_gates2", ptr(gx), ptr(gc), ptr(h), ptr(z), ptr(keep), ptr(cand), ptr(hnew),
+             ptr(hnext), B, H, stream_ptr())
+        ctx.save_for_backward(x, h, Wx, Wh, z, r, rh, cand, keep)
+        return hnew, hnext
+
+    @staticmethod
+    def backward(ctx, dhnew, dhnext):
+        x, h, Wx, Wh, z, r, rh, cand, keep = ctx.saved_tensors
+        B, H = h.shape
+        X = x.shape[1]
+        dev = x.device
+        dhnew = dhnew.contiguous() if dhnew is not None else None
+        dhnext = dhnext.contiguous() if dhnext is not None else None
+        dgx = torch.empty((B, 3 * H), dtype=torch.float32, device=dev)
+        dgc = torch.empty((B, H), dtype=torch.float32, device=dev)
+        dz, dh = torch.empty_like(dgc), torch.empty_like(dgc)
+        call("a2c_gru_gates2_bwd", ptr(dhnew), ptr(dhnext), ptr(keep), ptr(h), ptr(z), ptr(cand),
+             ptr(dgc), ptr(dz), ptr(dh), B, H, stream_ptr())
+        drh = gemm(dgc, H, 1, Wh[2], 1, H, B, H, H)          # dgc * Wh2^T
+        dgzr = torch.empty((B, 2 * H), dtype=torch.float32, device=dev)
+        call("a2c_gru_gates1_bwd", ptr(drh), ptr(dz), ptr(h), ptr(z), ptr(r), ptr(dgzr), ptr(dh), B, H,
+             stream_ptr())
+        dWx = torch.empty_like(Wx)
+        dWh = torch.empty_like(Wh)
+        db = torch.empty((3, 1, H), dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x)
+        # gate pre-activation grads: z, r live in dgzr[:, g*H:], candidate in dgc
+        gsrc = [(dgzr, 2 * H, 0), (dgzr, 2 * H, H), (dgc, H, 0)]
+        for g, (G, ld, off) in enumerate(gsrc):
+            Gp = G.view(-1)[off:]
+            # dx (+)= G_g * Wx[g]^T ; dh += G_g * Wh[g]^T (g < 2)
+            gemm(Gp, ld, 1, Wx[g], 1, H, B, X, H, out=dx, ldc=X, beta=0 if g == 0 else 1)
+            if g < 2:
+                gemm(Gp, ld, 1, Wh[g], 1, H, B, H, H, out=dh, ldc=H, beta=1)
+            # dWx[g] = x^T G_g ; dWh[g] = (h or r*h)^T G_g
+            gemm(x, 1, X, Gp, ld, 1, X, H, B, out=dWx, ldc=H, c_offset=g * X * H)
+            src = h if g < 2 else rh
+            gemm(src, 1, H, Gp, ld, 1, H, H, B, out=dWh, ldc=H, c_offset=g * H * H)
+        # bias grads: column sums of the three gate-gradient blocks, written in place
+        dbf = db.view(-1)
+        call("a2c_colsum", ptr(dgzr), ptr(dbf), B, 2 * H, stream_ptr())
+        call("a2c_colsum", ptr(dgc), ptr(dbf[2 * H:]), B, H, stream_ptr())
+        return dx, dh, dWx, dWh, db, None
+
+
+# --------------------------------------------------------------------------
+# clip + optimizer
+# --------------------------------------------------------------------------
+
+def grad_sumsq(flat_grad, out=None):
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float64, device=flat_grad.device)
+    call("a2c_grad_sumsq", ptr(flat_grad), ptr(out), flat_grad.numel(), stream_ptr())
+    return out
+
+
+def clip_optim_step(param, grad, state1, state2, sumsq, kind, lr, max_norm, step=1, alpha=0.99,
+                    eps=1e-8, beta1=0.9, beta2=0.999, zero_grad=True, norm_out=None):
+    cfg = OptimCfg(kind, 1 if zero_grad else 0, float(lr), float(max_norm), float(alpha),
+                   float(eps), float(beta1), float(beta2), int(step))
+    call("a2c_clip_optim_step", ptr(param), ptr(grad), ptr(state1), ptr(state2), ptr(sumsq),
+         C.byref(cfg), ptr(norm_out), param.numel(), stream_ptr())

@@ -43,6 +43,17 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / den)
 
 
+def compact_err(full, golden_compact):
+    """Error of a full tensor against its compactly stored golden value: the
+    L2 norm and the strided samples are compared separately (each relative to
+    its own scale) so a large norm cannot hide a wrong sample."""
+    full = np.asarray(full, dtype=np.float32).reshape(-1)
+    if full.size <= SAMPLE:
+        return rel_err(full, golden_compact)
+    c = compact(full)
+    return max(rel_err(c[:1], golden_compact[:1]), rel_err(c[1:], golden_compact[1:]))
+
+
 def params_for(model, fs, h, A=3):
     shapes = O.param_shapes(model, fs=fs, h=h, A=A)
     return OrderedDict((k, torch.from_numpy(v)) for k, v in

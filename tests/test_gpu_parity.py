@@ -1,0 +1,519 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the
+reference-generated golden fixtures.  Bit-exact for uint8 / index / scan work,
+<= 1e-5 relative (BASELINE.json north_star) for fp32."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import helpers as H
+from a2c_b200 import synth
+from oracle import a2c_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def ops_mod():
+    from a2c_b200 import ops
+    return ops
+
+
+# ---------------------------------------------------------------- stage 1 ----
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_obs_prep_bit_exact(dev, variant):
+    ops = ops_mod()
+    rng = np.random.default_rng(3)
+    frames = synth.make_frames(rng, 37)
+    frames[0][:] = 144
+    frames[1][:] = 109
+    frames[2][:] = 0
+    frames[3] = rng.integers(0, 256, size=frames[3].shape, dtype=np.uint8)   # pure noise
+    R, Fn = 1, 37
+    ring = ops.PlaneRing(R, Fn - 1, 1, dev)
+    reset = np.zeros((R, Fn), dtype=np.uint8)
+    ring.push_frames(torch.from_numpy(frames[None]).to(dev), torch.from_numpy(reset).to(dev),
+                     variant=variant)
+    got = ring.planes[0, :Fn].cpu().numpy().reshape(Fn, 80, 80)
+    want = np.stack([O.pong_prep(f)[0] for f in frames])
+    assert np.array_equal(got, want)
+    assert got[0].sum() == 0 and got[1].sum() == 0 and got[2].sum() == 0
+
+
+def test_obs_prep_golden_frames(dev):
+    ops = ops_mod()
+    g = H.load("units.npz")
+    rng = np.random.default_rng(int(g["prep_frames_seed"]))
+    frames = synth.make_frames(rng, 6)
+    frames[0][:] = 144
+    frames[1][:] = 109
+    frames[2][:] = 0
+    want = np.unpackbits(g["prep_out_bits"])[:6 * 6400].reshape(6, 80, 80)
+    ring = ops.PlaneRing(6, 1, 1, dev)
+    ring.push_frames(torch.from_numpy(frames[:, None]).to(dev),
+                     torch.ones((6, 1), dtype=torch.uint8, device=dev))
+    assert np.array_equal(ring.planes[:, 0].cpu().numpy().reshape(6, 80, 80), want)
+
+
+def test_pong_prep_callable_matches_reference_signature(dev):
+    from a2c_b200 import preprocessing
+    rng = np.random.default_rng(9)
+    f = synth.make_frames(rng, 1)[0]
+    out = preprocessing.pong_prep(f)
+    assert out.shape == (1, 80, 80) and out.dtype == np.uint8
+    assert np.array_equal(out, O.pong_prep(f))
+
+
+@pytest.mark.parametrize("fs", [1, 2, 3, 4])
+@pytest.mark.parametrize("host", [False, True])
+def test_ring_stack_with_resets_and_carry(dev, fs, host):
+    ops = ops_mod()
+    R, T = 5, 7
+    t0 = synth.make_trajectory(R, T, seed=11, p_reset=0.3)
+    t1 = synth.make_trajectory(R, T, seed=12, p_reset=0.3, first_rollout=False)
+    frames, reset = H.chain_frames([t0, t1])
+    want = O.prep_and_stack(frames, reset, fs)              # [R, 2T+1, fs, 80, 80]
+    ring = ops.PlaneRing(R, T, fs, dev)
+
+    def put(x):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+        return x.pin_memory() if host else x.to(dev)
+    ring.push_frames(put(t0["frames"]), put(t0["reset"]))
+    got0 = ring.view(T + 1).materialize(torch.uint8).cpu().numpy().reshape(R, T + 1, fs, 80, 80)
+    assert np.array_equal(got0, want[:, :T + 1])
+    f32 = ring.view(T).materialize(torch.float32).cpu().numpy().reshape(R, T, fs, 80, 80)
+    assert np.array_equal(f32, want[:, :T].astype(np.float32))
+    ring.carry()
+    ring.push_frames(put(t1["frames"][:, 1:]), put(t1["reset"][:, 1:]), first_frame_index=1)
+    got1 = ring.view(T + 1).materialize(torch.uint8).cpu().numpy().reshape(R, T + 1, fs, 80, 80)
+    assert np.array_equal(got1, want[:, T:])
+
+
+def test_prep_empty_and_single(dev):
+    ops = ops_mod()
+    ring = ops.PlaneRing(3, 4, 2, dev)
+    ring.push_frames(torch.zeros((3, 0, 210, 160, 3), dtype=torch.uint8, device=dev),
+                     torch.zeros((3, 0), dtype=torch.uint8, device=dev))
+    assert int(ring.planes.sum()) == 0
+    with pytest.raises(Exception):
+        ring.push_frames(torch.zeros((3, 9, 210, 160, 3), dtype=torch.uint8, device=dev),
+                         torch.zeros((3, 9), dtype=torch.uint8, device=dev))   # overflows the ring
+
+
+def test_prep_full_size_checksum(dev):
+    """C2-sized batch: plane population must equal the oracle's on a sampled
+    subset and the idempotence property prep(prep-like frame) holds."""
+    ops = ops_mod()
+    R, T = 256, 20
+    g = torch.Generator(device="cpu").manual_seed(5)
+    frames = torch.randint(0, 256, (R, T + 1, 210, 160, 3), dtype=torch.uint8, generator=g)
+    bg = torch.rand((R, T + 1, 210, 160, 3), generator=g) < 0.9
+    frames[bg] = 144
+    ring = ops.PlaneRing(R, T, 2, dev)
+    reset = torch.zeros((R, T + 1), dtype=torch.uint8)
+    ring.push_frames(frames.to(dev), reset.to(dev))
+    got = ring.planes[:, 1:].cpu().numpy().reshape(R, T + 1, 80, 80)
+    idx = [(0, 0), (17, 3), (255, 20), (100, 11)]
+    for r, t in idx:
+        assert np.array_equal(got[r, t], O.pong_prep(frames[r, t].numpy())[0])
+    sel = frames[:, :, 35:195:2, ::2, 0]
+    want_count = int(((sel != 0) & (sel != 144) & (sel != 109)).sum())
+    assert int(got.sum()) == want_count
+
+
+# ------------------------------------------------------------- acting -------
+
+def test_sample_action_bit_exact(dev):
+    ops = ops_mod()
+    g = H.load("units.npz")
+    got = ops.sample_action(torch.from_numpy(g["sa_pi"]).to(dev), torch.from_numpy(g["sa_u"]).to(dev),
+                            is_prob=True).cpu().numpy()
+    assert np.array_equal(got, g["sa_act"].astype(np.int64))
+    assert got[0] == -1
+    from a2c_b200 import utils
+    out = utils.sample_action(torch.from_numpy(g["sa_pi"]), rand_nums=torch.from_numpy(g["sa_u"]))
+    assert out.dtype == torch.float32 and np.array_equal(out.numpy(), g["sa_act"])
+
+
+def test_sample_action_from_logits(dev):
+    ops = ops_mod()
+    gen = torch.Generator().manual_seed(4)
+    logits = torch.randn(20000, 3, generator=gen) * 3
+    u = torch.rand(20000, generator=gen)
+    want = O.get_action(logits, u)
+    got = ops.sample_action(logits.to(dev), u.to(dev)).cpu()
+    # softmax rounding may differ in the last ulp; indices must agree except on
+    # exact-boundary draws, of which there are none at this size
+    assert (got != want).sum().item() <= 1
+
+
+# ---------------------------------------------------------------- stage 2 ----
+
+def test_discount_known_answer_and_golden(dev):
+    from a2c_b200 import utils
+    g = H.load("units.npz")
+    out = utils.discount(torch.tensor([1., 1, 1]), torch.tensor([0., 0, 1]), .5)
+    assert not out.is_cuda and np.array_equal(out.numpy(), np.array([1.75, 1.5, 1.0], np.float32))
+    for key, f in (("disc_out_g99", 0.99), ("disc_out_gl", 0.99 * 0.98)):
+        got = utils.discount(torch.from_numpy(g["disc_arr"]), torch.from_numpy(g["disc_dones"]), f)
+        assert np.array_equal(got.numpy(), g[key])
+
+
+@pytest.mark.parametrize("N,p", [(1, 0.0), (7, 0.0), (1000, 0.05), (81920, 0.1), (4096, 1.0)])
+def test_discount_random_bit_exact(dev, N, p):
+    ops = ops_mod()
+    gen = torch.Generator().manual_seed(N)
+    a = torch.randn(N, generator=gen)
+    d = (torch.rand(N, generator=gen) < p).float()
+    stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    got = ops.discount(a.to(dev), d.to(dev), 0.99 * 0.98, stats=stats).cpu()
+    want = O.discount(a, d, 0.99 * 0.98)
+    assert torch.equal(got, want)
+    assert abs(stats[0].item() - want.double().sum().item()) < 1e-6 * max(1, N)
+    assert abs(stats[1].item() - (want.double() ** 2).sum().item()) < 1e-6 * max(1, N)
+
+
+@pytest.mark.parametrize("R,T", [(1, 1), (4, 15), (3, 2), (256, 20), (1024, 20), (512, 32), (130, 5)])
+def test_delta_scan_bit_exact(dev, R, T):
+    ops = ops_mod()
+    traj = synth.make_trajectory(R, T, seed=R * 100 + T, with_frames=False, p_reset=0.05)
+    done = ((traj["reset"][:, 1:] != 0) | (traj["rewards"] != 0)).astype(np.float32)
+    r2, d2, want_deltas = O.rollout_bookkeeping(traj["rewards"], done, traj["values"], 0.99)
+    rew = torch.from_numpy(traj["rewards"].reshape(-1).copy()).to(dev)
+    dn = torch.from_numpy(done.reshape(-1).copy()).to(dev)
+    deltas, advs, rets, stats = ops.delta_scan(rew, dn, torch.from_numpy(traj["values"]).to(dev),
+                                               0.99, 0.98)
+    assert torch.equal(rew.cpu(), r2.reshape(-1))
+    assert torch.equal(dn.cpu(), d2.reshape(-1))
+    assert torch.equal(deltas.cpu(), want_deltas.reshape(-1))
+    want_advs = O.discount(want_deltas, d2, 0.99 * 0.98)
+    want_rets = O.discount(r2, d2, 0.99)
+    assert torch.equal(advs.cpu(), want_advs)
+    assert torch.equal(rets.cpu(), want_rets)
+    assert abs(stats[0].item() - want_advs.double().sum().item()) < 1e-6 * R * T
+    # every segment ends with done = 1 (runner.py:243)
+    assert bool((dn.view(R, T)[:, -1] == 1).all())
+
+
+# ---------------------------------------------------------------- stage 3 ----
+
+@pytest.mark.parametrize("N,A,norm,nstep", [(60, 3, True, False), (5120, 3, True, False),
+                                            (333, 3, False, True), (2048, 6, True, True)])
+def test_loss_fwd_bwd(dev, N, A, norm, nstep):
+    ops = ops_mod()
+    gen = torch.Generator().manual_seed(N + A)
+    logits = (torch.randn(N, A, generator=gen) * 2).requires_grad_(True)
+    vals = torch.randn(N, 1, generator=gen).requires_grad_(True)
+    actions = torch.randint(0, A, (N,), generator=gen)
+    actions[0] = -1                                     # the sample_action "-1" edge
+    advs = torch.randn(N, generator=gen)
+    rets = torch.randn(N, generator=gen)
+    hyps = dict(pi_coef=1.0, val_coef=0.5, entr_coef=0.005, norm_advs=norm, use_nstep_rets=nstep)
+    a_n = (advs - advs.mean()) / (advs.std() + 1e-6) if norm else advs
+    r_n = advs + vals.detach().squeeze() if nstep else rets
+    loss, pi_l, val_l, ent_l = O.a2c_loss(logits, vals, actions, a_n, r_n, hyps)
+    loss.backward()
+    stats = torch.tensor([advs.double().sum(), (advs.double() ** 2).sum()], dtype=torch.float64)
+    dl, dv, out = ops.loss_fwd_bwd(logits.detach().to(dev), vals.detach().to(dev), actions.to(dev),
+                                   advs.to(dev), rets.to(dev), stats.to(dev), hyps)
+    want = [loss.item(), pi_l.item(), val_l.item(), ent_l.item()]
+    for a, b in zip(out.tolist(), want):
+        assert abs(a - b) <= TOL * max(1.0, abs(b))
+    assert H.rel_err(dl.cpu().numpy(), logits.grad.numpy()) < TOL
+    assert H.rel_err(dv.cpu().numpy(), vals.grad.numpy().reshape(-1)) < TOL
+
+
+# ---------------------------------------------------------------- stage 4 ----
+
+@pytest.mark.parametrize("M,N,K,ta,tb", [
+    (128, 128, 64, False, False), (60, 256, 12800, False, True), (5, 3, 7, True, False),
+    (300, 200, 100, True, True), (256, 3, 256, False, True), (2000, 130, 513, False, False),
+    (3, 256, 5120, True, False), (129, 257, 31, False, True)])
+def test_gemm_fp32(dev, M, N, K, ta, tb):
+    ops = ops_mod()
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=gen)
+    B = torch.randn((N, K) if tb else (K, N), generator=gen)
+    bias = torch.randn(N, generator=gen)
+    Am = A.t() if ta else A
+    Bm = B.t() if tb else B
+    want = (Am.double() @ Bm.double() + bias.double()).clamp_min(0).float()
+    sam, sak = (1, M) if ta else (K, 1)
+    sbk, sbn = (1, K) if tb else (N, 1)
+    got = ops.gemm(A.to(dev), sam, sak, B.to(dev), sbk, sbn, M, N, K, bias=bias.to(dev), relu=True,
+                   precision=0)
+    assert H.rel_err(got.cpu().numpy(), want.numpy()) < TOL
+    # beta = 1 accumulates
+    got2 = ops.gemm(A.to(dev), sam, sak, B.to(dev), sbk, sbn, M, N, K, out=got.clone(), ldc=N, beta=1,
+                    precision=0)
+    want2 = want.double() + Am.double() @ Bm.double()
+    assert H.rel_err(got2.cpu().numpy(), want2.numpy()) < TOL
+
+
+CONVS = [  # Cin, Cout, H, K, stride, pad  -- every layer shape of the four models
+    (2, 16, 80, 3, 1, 1), (16, 24, 80, 3, 1, 1), (24, 32, 80, 3, 2, 1), (32, 64, 40, 3, 2, 1),
+    (16, 24, 80, 3, 2, 1), (24, 32, 40, 3, 2, 1), (32, 48, 20, 3, 2, 1), (48, 64, 10, 3, 2, 1),
+    (2, 16, 80, 8, 4, 0), (16, 32, 19, 4, 2, 0), (3, 16, 80, 3, 1, 1)]
+
+
+@pytest.mark.parametrize("Cin,Cout,Hh,K,S,P", CONVS)
+def test_conv_fwd_bwd(dev, Cin, Cout, Hh, K, S, P):
+    ops = ops_mod()
+    gen = torch.Generator().manual_seed(Cin * 100 + Cout + K)
+    Nb = 3
+    x = torch.randn(Nb, Cin, Hh, Hh, generator=gen).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, K, K, generator=gen) / np.sqrt(Cin * K * K)).requires_grad_(True)
+    b = torch.randn(Cout, generator=gen).requires_grad_(True)
+    y = F.relu(F.conv2d(x.double(), w.double(), b.double(), stride=S, padding=P))
+    gy = torch.randn(y.shape, generator=gen)
+    y.backward(gy.double())
+    xd = x.detach().to(dev).requires_grad_(True)
+    wd = w.detach().to(dev).requires_grad_(True)
+    bd = b.detach().to(dev).requires_grad_(True)
+    yd = ops.Conv2dFn.apply(xd, wd, bd, S, P, True)
+    assert H.rel_err(yd.detach().cpu().numpy(), y.detach().numpy()) < TOL
+    yd.backward(gy.to(dev))
+    assert H.rel_err(xd.grad.cpu().numpy(), x.grad.numpy()) < TOL
+    assert H.rel_err(wd.grad.cpu().numpy(), w.grad.numpy()) < TOL
+    assert H.rel_err(bd.grad.cpu().numpy(), b.grad.numpy()) < TOL
+
+
+def test_conv_first_layer_reads_ring(dev):
+    ops = ops_mod()
+    R, T, fs = 3, 4, 2
+    traj = synth.make_trajectory(R, T, seed=2, p_reset=0.3)
+    ring = ops.PlaneRing(R, T, fs, dev)
+    ring.push_frames(torch.from_numpy(traj["frames"]).to(dev), torch.from_numpy(traj["reset"]).to(dev))
+    states = torch.from_numpy(O.prep_and_stack(traj["frames"], traj["reset"], fs)[:, :T]
+                              .reshape(R * T, fs, 80, 80)).float()
+    gen = torch.Generator().manual_seed(0)
+    w = torch.randn(16, fs, 3, 3, generator=gen).requires_grad_(True)
+    b = torch.randn(16, generator=gen).requires_grad_(True)
+    y = F.relu(F.conv2d(states, w, b, padding=1))
+    gy = torch.randn(y.shape, generator=gen)
+    y.backward(gy)
+    wd = w.detach().to(dev).requires_grad_(True)
+    bd = b.detach().to(dev).requires_grad_(True)
+    yd = ops.Conv2dFn.apply(ring.view(T), wd, bd, 1, 1, True)
+    assert H.rel_err(yd.detach().cpu().numpy(), y.detach().numpy()) < TOL
+    yd.backward(gy.to(dev))
+    assert H.rel_err(wd.grad.cpu().numpy(), w.grad.numpy()) < TOL
+    assert H.rel_err(bd.grad.cpu().numpy(), b.grad.numpy()) < TOL
+
+
+def test_layernorm(dev):
+    ops = ops_mod()
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(77, 256, generator=gen).requires_grad_(True)
+    gm = torch.randn(256, generator=gen).requires_grad_(True)
+    bt = torch.randn(256, generator=gen).requires_grad_(True)
+    y = F.layer_norm(x, (256,), gm, bt)
+    gy = torch.randn(y.shape, generator=gen)
+    y.backward(gy)
+    xd, gd, bd = (t.detach().to(dev).requires_grad_(True) for t in (x, gm, bt))
+    yd = ops.LayerNormFn.apply(xd, gd, bd)
+    yd.backward(gy.to(dev))
+    assert H.rel_err(yd.detach().cpu().numpy(), y.detach().numpy()) < TOL
+    for a, b_ in ((xd, x), (gd, gm), (bd, bt)):
+        assert H.rel_err(a.grad.cpu().numpy(), b_.grad.numpy()) < TOL
+
+
+def test_gru_cell(dev):
+    ops = ops_mod()
+    gen = torch.Generator().manual_seed(2)
+    B, Hd = 37, 64
+    p = {"gru.W_x": torch.randn(3, Hd, Hd, generator=gen) / 8,
+         "gru.W_h": torch.randn(3, Hd, Hd, generator=gen) / 8,
+         "gru.b": torch.randn(3, 1, Hd, generator=gen)}
+    p = {k: v.requires_grad_(True) for k, v in p.items()}
+    x = torch.randn(B, Hd, generator=gen).requires_grad_(True)
+    h = torch.randn(B, Hd, generator=gen).requires_grad_(True)
+    keep = (torch.rand(B, generator=gen) < 0.7).float()
+    hn = O.gru_cell(p, x, h)
+    g1, g2 = torch.randn(B, Hd, generator=gen), torch.randn(B, Hd, generator=gen)
+    (hn * g1 + hn * keep[:, None] * g2).sum().backward()
+    d = {k: v.detach().to(dev).requires_grad_(True) for k, v in p.items()}
+    xd, hd = x.detach().to(dev).requires_grad_(True), h.detach().to(dev).requires_grad_(True)
+    hnew, hnext = ops.GRUCellFn.apply(xd, hd, d["gru.W_x"], d["gru.W_h"], d["gru.b"], keep.to(dev))
+    assert H.rel_err(hnew.detach().cpu().numpy(), hn.detach().numpy()) < TOL
+    assert H.rel_err(hnext.detach().cpu().numpy(), (hn * keep[:, None]).detach().numpy()) < TOL
+    (hnew * g1.to(dev) + hnext * g2.to(dev)).sum().backward()
+    assert H.rel_err(xd.grad.cpu().numpy(), x.grad.numpy()) < TOL
+    assert H.rel_err(hd.grad.cpu().numpy(), h.grad.numpy()) < TOL
+    for k in p:
+        assert H.rel_err(d[k].grad.cpu().numpy(), p[k].grad.numpy()) < TOL, k
+
+
+# ------------------------------------------------ models / Updater / Runner ----
+
+def build_net(model, fs, h, dev):
+    from a2c_b200 import models
+    net = models.get_model_class(model)([fs, 80, 80], 3, h_size=h, bnorm=False, is_discrete=True)
+    missing, unexpected = net.load_state_dict(H.params_for(model, fs, h), strict=False)
+    assert not unexpected
+    return net.to(dev)
+
+
+def test_state_dict_keys_match_reference_names(dev):
+    """Checkpoint interchange: same keys / shapes as the reference modules."""
+    for model in ("FCModel", "A3CModel", "ConvModel", "GRUModel"):
+        net = build_net(model, 2, 32, dev)
+        sd = net.state_dict()
+        for k, shape in O.param_shapes(model, 2, 32).items():
+            assert k in sd and tuple(sd[k].shape) == tuple(shape), (model, k)
+    sd = build_net("A3CModel", 2, 32, dev).state_dict()
+    for k in ("conv1.0.weight", "features.1.0.bias", "emb_bnorm.running_mean"):
+        assert k in sd
+    from a2c_b200 import models
+    assert models.get_model_class("conv") is models.ConvModel
+
+
+SMALL = [("c1_fc.npz", "FCModel", 4, 15, 2, 256),
+         ("small_a3c.npz", "A3CModel", 3, 6, 2, 64),
+         ("small_conv.npz", "ConvModel", 3, 6, 2, 32),
+         ("small_gru.npz", "GRUModel", 3, 6, 2, 64),
+         ("small_gru_bptt.npz", "GRUModel", 3, 6, 2, 64),
+         ("small_fc_adam_nstep.npz", "FCModel", 3, 6, 2, 64),
+         ("small_fc_fs3.npz", "FCModel", 3, 6, 3, 64)]
+
+
+@pytest.mark.parametrize("fname,model,R,T,fs,h", SMALL)
+def test_runner_and_updater_against_reference_golden(dev, fname, model, R, T, fs, h):
+    """The drop-in path end to end: batched Runner.rollout + Updater.update_model,
+    two consecutive updates, against the unmodified reference's outputs."""
+    from a2c_b200 import runner as runner_mod, updater as updater_mod
+    g = H.load(fname)
+    hyps = H.hyps_of(g)
+    hyps["preprocessor"] = None
+    trajs = H.small_trajectories(g, R, T)
+    net = build_net(model, fs, h, dev)
+    datas = runner_mod.make_shared_data(R, T, fs, dev, h_size=h if net.is_recurrent else None)
+    run = runner_mod.Runner(datas, hyps, None, None, None)
+    env = runner_mod.RecordedVecEnv(trajs[0], dev)
+    run.attach(net, env)
+    upd = updater_mod.Updater(net, hyps)
+    N = R * T
+    for k, traj in enumerate(trajs):
+        if k > 0:
+            env.load(traj)
+        run.rollout(net, 0, hyps)
+        pre = "u%d_" % k
+        assert np.array_equal(datas["states"].cpu().numpy().astype(np.uint8),
+                              H.golden_states(g, k, N, fs))
+        assert np.array_equal(datas["actions"].cpu().numpy(), g[pre + "actions"])
+        assert np.array_equal(datas["dones"].cpu().numpy(), g[pre + "dones"])
+        for key in ("rewards", "deltas") + (("h_states",) if "h_states" in datas else ()):
+            assert H.rel_err(datas[key].cpu().numpy(), g[pre + key]) < TOL, key
+        # isolate update parity from acting noise: feed the reference's recorded datas
+        shared = {key: torch.from_numpy(g[pre + key]).to(dev) for key in
+                  ("rewards", "dones", "deltas", "actions")}
+        shared["states_view"] = datas["states_view"]
+        shared["states"] = datas["states"]
+        if "h_states" in datas:
+            shared["h_states"] = torch.from_numpy(g[pre + "h_states"]).to(dev)
+        res = upd.compute_gradients(shared)
+        grads = {name: p.grad.detach().clone() for name, p in net.named_parameters()}
+        for name in O.param_shapes(model, fs, h):
+            key = pre + "grad/" + name
+            if key in g:
+                assert H.compact_err(grads[name].cpu().numpy(), g[key]) < TOL, name
+        upd._optim_step()
+        terms = res["loss_terms"].tolist()
+        for i, key in enumerate(("Loss", "Pi_Loss", "ValLoss", "Entropy")):
+            assert abs(terms[i] - float(g[pre + key])) <= TOL * max(1.0, abs(float(g[pre + key]))), key
+        assert abs(upd.flat.norm.item() - float(g[pre + "GradNorm"])) <= TOL * max(1.0, float(g[pre + "GradNorm"]))
+        params = dict(net.named_parameters())
+        for name in O.param_shapes(model, fs, h):
+            assert H.compact_err(params[name].detach().cpu().numpy(),
+                             g[pre + "param_after/" + name]) < TOL, name
+
+
+def test_updater_accepts_reference_layout_fp32_states(dev):
+    """Drop-in: the reference's own shared_data layout (fp32 states tensor,
+    CPU LongTensor actions) gives the same update as the ring view."""
+    from a2c_b200 import updater as updater_mod
+    g = H.load("small_conv.npz")
+    hyps = H.hyps_of(g)
+    R, T, fs, h = 3, 6, 2, 32
+    N = R * T
+    net = build_net("ConvModel", fs, h, dev)
+    upd = updater_mod.Updater(net, hyps)
+    shared = {"states": torch.from_numpy(H.golden_states(g, 0, N, fs)).float().to(dev),
+              "rewards": torch.from_numpy(g["u0_rewards"]).to(dev),
+              "dones": torch.from_numpy(g["u0_dones"]).to(dev),
+              "deltas": torch.from_numpy(g["u0_deltas"]).to(dev),
+              "actions": torch.from_numpy(g["u0_actions"])}          # CPU, as training.py:97
+    info = upd.update_model(shared)
+    assert set(info) == {"Loss", "Pi_Loss", "ValLoss", "Entropy", "GradNorm"}
+    assert isinstance(info["Loss"], float) and torch.is_tensor(info["GradNorm"])
+    for key in ("Loss", "Pi_Loss", "ValLoss", "Entropy"):
+        assert abs(info[key] - float(g["u0_" + key])) <= TOL * max(1.0, abs(float(g["u0_" + key])))
+    params = dict(net.named_parameters())
+    for name in O.param_shapes("ConvModel", fs, h):
+        assert H.compact_err(params[name].detach().cpu().numpy(),
+                         g["u0_param_after/" + name]) < TOL, name
+
+
+FULL = [("full_c3_a3c.npz", "A3CModel", 1024, 20), ("full_c4_gru_bptt.npz", "GRUModel", 512, 32),
+        ("full_c2_conv.npz", "ConvModel", 256, 20)]
+
+
+@pytest.mark.parametrize("fname,model,R,T", FULL)
+def test_full_size_update_against_reference_golden(dev, fname, model, R, T):
+    """BASELINE configs C2-C4 at full size: stage 1 from raw frames on the GPU,
+    then Updater.update_model, against the unmodified reference's outputs."""
+    from a2c_b200 import ops, updater as updater_mod
+    g = H.load(fname)
+    hyps = H.hyps_of(g)
+    fs, h = 2, 256
+    N = R * T
+    traj = synth.make_trajectory(R, T, seed=int(g["seed"]))
+    ring = ops.PlaneRing(R, T, fs, dev)
+    ring.push_frames(torch.from_numpy(traj["frames"]).to(dev), torch.from_numpy(traj["reset"]).to(dev))
+    view = ring.view(T)
+    assert abs(float(view.materialize(torch.uint8).sum(dtype=torch.float64)) - float(g["states_sum"])) < 0.5
+    done = ((traj["reset"][:, 1:] != 0) | (traj["rewards"] != 0)).astype(np.float32)
+    rew = torch.from_numpy(traj["rewards"].reshape(-1).copy()).to(dev)
+    dn = torch.from_numpy(done.reshape(-1).copy()).to(dev)
+    deltas, advs, rets, _ = ops.delta_scan(rew, dn, torch.from_numpy(traj["values"]).to(dev),
+                                           hyps["gamma"], hyps["lambda_"])
+    assert H.rel_err(H.compact(advs.cpu().numpy()), g["advs"]) == 0.0      # bit-exact scans
+    assert H.rel_err(H.compact(rets.cpu().numpy()), g["returns"]) == 0.0
+    rng = np.random.default_rng(int(g["seed"]) + 1)
+    actions = torch.from_numpy(rng.integers(0, 3, size=N)).long()
+    shared = {"states_view": view, "states": None, "rewards": rew, "dones": dn, "deltas": deltas,
+              "actions": actions.to(dev)}
+    net = build_net(model, fs, h, dev)
+    if model == "GRUModel":
+        shared["h_states"] = torch.from_numpy(synth.hashed_tensor((N, h), 999, 0.5)).float().to(dev)
+    upd = updater_mod.Updater(net, hyps)
+    res = upd.compute_gradients(shared)
+    grads = {name: p.grad.detach().clone() for name, p in net.named_parameters()}
+    for name in O.param_shapes(model, fs, h):
+        key = "grad/" + name
+        if key in g:
+            assert H.compact_err(grads[name].cpu().numpy(), g[key]) < TOL, name
+    upd._optim_step()
+    terms = res["loss_terms"].tolist()
+    for i, key in enumerate(("Loss", "Pi_Loss", "ValLoss", "Entropy")):
+        assert abs(terms[i] - float(g[key])) <= TOL * max(1.0, abs(float(g[key]))), key
+    assert abs(upd.flat.norm.item() - float(g["GradNorm"])) <= TOL * max(1.0, float(g["GradNorm"]))
+    params = dict(net.named_parameters())
+    for name in O.param_shapes(model, fs, h):
+        assert H.compact_err(params[name].detach().cpu().numpy(),
+                         g["param_after/" + name]) < TOL, name
+
+
+def test_launches_come_from_our_library(dev):
+    from a2c_b200 import _lib, ops
+    n0 = _lib.launch_count()
+    ops.discount(torch.ones(8, device=dev), torch.zeros(8, device=dev), 0.5)
+    assert _lib.launch_count() == n0 + 1
