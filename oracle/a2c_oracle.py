@@ -296,10 +296,13 @@ class UpdaterOracle:
     """a2c/updater.py:9-137.  ``compute`` is update_model up to and including
     loss.backward() + clip_grad_norm_; ``step`` adds optimizer.step()."""
 
-    def __init__(self, model, params, hyps):
+    def __init__(self, model, params, hyps, dtype=torch.float32):
+        # dtype=float64 evaluates the same algorithm in double (scans stay fp32,
+        # they are bit-exact by construction): the yardstick for ill-conditioned sums
         self.model = model
         self.hyps = hyps
-        self.p = OrderedDict((k, torch.as_tensor(v, dtype=torch.float32).clone()
+        self.dtype = dtype
+        self.p = OrderedDict((k, torch.as_tensor(v).to(dtype).clone()
                               .requires_grad_(True)) for k, v in params.items())
         self.optim = getattr(torch.optim, hyps["optim_type"])(
             list(self.p.values()), lr=hyps["lr"])            # :226-229
@@ -308,24 +311,25 @@ class UpdaterOracle:
 
     def forward(self, shared):
         hyps = self.hyps
-        states = shared["states"].float()
+        states = shared["states"].to(self.dtype)
         if is_recurrent(self.model):
+            hs = shared["h_states"].to(self.dtype)
             if hyps["use_bptt"]:                             # :76
-                return bptt(self.model, self.p, states, shared["h_states"],
-                            shared["dones"], hyps["n_rollouts"], hyps["n_tsteps"])
-            v, l, _ = model_forward(self.model, self.p, states, shared["h_states"])  # :78
+                return bptt(self.model, self.p, states, hs, shared["dones"].to(self.dtype),
+                            hyps["n_rollouts"], hyps["n_tsteps"])
+            v, l, _ = model_forward(self.model, self.p, states, hs)  # :78
             return v, l
         return model_forward(self.model, self.p, states)     # :80
 
     def compute(self, shared):
         hyps = self.hyps
         dones = shared["dones"].reshape(-1)
-        advs = discount(shared["deltas"], dones, hyps["gamma"] * hyps["lambda_"])  # :70
+        advs = discount(shared["deltas"], dones, hyps["gamma"] * hyps["lambda_"]).to(self.dtype)  # :70
         vals, logits = self.forward(shared)
         if hyps["use_nstep_rets"]:                           # :83-84
             returns = advs + vals.detach().reshape(-1)
         else:                                                # :86-88
-            returns = discount(shared["rewards"], dones, hyps["gamma"])
+            returns = discount(shared["rewards"], dones, hyps["gamma"]).to(self.dtype)
         raw_advs, raw_returns = advs.clone(), returns.clone()
         if hyps.get("norm_returns", False):                  # :89-96
             if self.ret_mean is None:

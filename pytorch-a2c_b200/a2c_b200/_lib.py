@@ -100,10 +100,24 @@ def load():
     return lib
 
 
-def call(name, *args):
-    """Calls an entry point; raises A2CError with the library's message on failure."""
+# bench.py sets PROFILE = {} to time calls in place: {tag: [(start_evt, end_evt, work), ...]}
+# with CUDA events recorded on the launching (current) stream around the C-ABI call.
+PROFILE = None
+
+
+def call(name, *args, tag=None, work=0):
+    """Calls an entry point; raises A2CError with the library's message on failure.
+    tag / work (flops or bytes the launch performs) feed the optional profiler."""
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if PROFILE is not None and tag is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args)
+        e1.record()
+        PROFILE.setdefault(tag, []).append((e0, e1, work))
+    else:
+        rc = getattr(lib, name)(*args)
     if name in _NO_STATUS:
         return rc
     if rc != 0:

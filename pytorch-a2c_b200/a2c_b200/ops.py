@@ -97,11 +97,14 @@ class PlaneRing:
         assert R == self.R and frames.shape[2:] == (210, 160, 3) and frames.dtype == torch.uint8
         assert reset.shape == (R, F) and reset.dtype == torch.uint8
         assert frames.is_contiguous() and reset.is_contiguous()
+        if F == 0:
+            return
         j0 = self.fs - 1 + first_frame_index
         if frames.is_cuda:
             require_cuda(reset)
             call("a2c_obs_prep_stack", ptr(frames), ptr(reset), ptr(self.planes), ptr(self.pflag),
-                 R, F, self.P, j0, variant, stream_ptr())
+                 R, F, self.P, j0, variant, stream_ptr(),
+                 tag="a2c_obs_prep_stack|bytes|%dx%d" % (R, F), work=44800 * R * F)
         else:
             if not (frames.is_pinned() and reset.is_pinned()):
                 raise _lib.A2CError("host frames / reset must be pinned (tensor.pin_memory())")
@@ -202,7 +205,7 @@ def gemm(A, sam, sak, B, sbk, sbn, M, N, K, out=None, ldc=None, bias=None, relu=
     cptr = C.c_void_p(out.data_ptr() + 4 * c_offset)
     call("a2c_gemm", ptr(A), sam, sak, ptr(B), sbk, sbn, cptr, ldc, ptr(bias), M, N, K,
          1 if relu else 0, beta, _PRECISION if precision is None else precision, ptr(ws),
-         ws.numel(), stream_ptr())
+         ws.numel(), stream_ptr(), tag="a2c_gemm|flops|%dx%dx%d" % (M, N, K), work=2.0 * M * N * K)
     return out
 
 
@@ -261,7 +264,8 @@ class LinearStateFn(torch.autograd.Function):
         assert W.shape[1] == view.fs * PLANE and W.is_contiguous()
         y = torch.empty((view.N, N), dtype=torch.float32, device=W.device)
         call("a2c_linear_state_fwd", C.byref(view.c), ptr(W), ptr(b), ptr(y), view.R, N,
-             1 if relu else 0, stream_ptr())
+             1 if relu else 0, stream_ptr(), tag="a2c_linear_state_fwd|flops|%dx%d" % (view.N, N),
+             work=2.0 * view.N * N * view.fs * PLANE)
         ctx.view = view
         ctx.save_for_backward(W, y if relu else None)
         ctx.relu = relu
@@ -280,7 +284,8 @@ class LinearStateFn(torch.autograd.Function):
             dW = torch.empty_like(W)
             ws = workspace(W.device)
             call("a2c_linear_state_wgrad", C.byref(view.c), ptr(dy), ptr(dW), view.R, N, ptr(ws),
-                 ws.numel(), stream_ptr())
+                 ws.numel(), stream_ptr(), tag="a2c_linear_state_wgrad|flops|%dx%d" % (view.N, N),
+                 work=2.0 * view.N * N * view.fs * PLANE)
         if ctx.needs_input_grad[2]:
             db = colsum(dy, view.N, N)
         return None, dW, db, None
@@ -309,8 +314,12 @@ class Conv2dFn(torch.autograd.Function):
             N, _, H, Wd = x.shape
         s = conv_shape(Cin, Cout, H, Wd, K, stride, pad)
         y = torch.empty((N, Cout, s.OH, s.OW), dtype=torch.float32, device=W.device)
+        flops = 2.0 * N * s.OH * s.OW * Cout * Cin * K * K
+        sig = "%d:%d>%d,%dx%d,k%ds%d" % (N, Cin, Cout, H, Wd, K, stride)
         call("a2c_conv2d_fwd", None if is_view else ptr(x), C.byref(x.c) if is_view else None,
-             ptr(W), ptr(b), ptr(y), N, C.byref(s), 1 if relu else 0, stream_ptr())
+             ptr(W), ptr(b), ptr(y), N, C.byref(s), 1 if relu else 0, stream_ptr(),
+             tag="a2c_conv2d_fwd|flops|" + sig, work=flops)
+        ctx.flops, ctx.sig = flops, sig
         ctx.shape, ctx.relu, ctx.is_view, ctx.N = s, relu, is_view, N
         if is_view:
             ctx.view = x
@@ -333,7 +342,7 @@ class Conv2dFn(torch.autograd.Function):
         if not ctx.is_view and ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             call("a2c_conv2d_bwd_data", ptr(dy), ptr(mask), ptr(W), ptr(dx), N, C.byref(s),
-                 stream_ptr())
+                 stream_ptr(), tag="a2c_conv2d_bwd_data|flops|" + ctx.sig, work=ctx.flops)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             dW = torch.empty_like(W)
             db = torch.empty(s.Cout, dtype=torch.float32, device=W.device)
@@ -341,7 +350,7 @@ class Conv2dFn(torch.autograd.Function):
             ws = workspace(W.device, max(need, 64 << 20))
             call("a2c_conv2d_bwd_weight", ptr(x), C.byref(ctx.view.c) if ctx.is_view else None,
                  ptr(dy), ptr(mask), ptr(dW), ptr(db), N, C.byref(s), ptr(ws), ws.numel(),
-                 stream_ptr())
+                 stream_ptr(), tag="a2c_conv2d_bwd_weight|flops|" + ctx.sig, work=ctx.flops)
         return dx, dW, db, None, None, None
 
 
@@ -460,4 +469,6 @@ def clip_optim_step(param, grad, state1, state2, sumsq, kind, lr, max_norm, step
     cfg = OptimCfg(kind, 1 if zero_grad else 0, float(lr), float(max_norm), float(alpha),
                    float(eps), float(beta1), float(beta2), int(step))
     call("a2c_clip_optim_step", ptr(param), ptr(grad), ptr(state1), ptr(state2), ptr(sumsq),
-         C.byref(cfg), ptr(norm_out), param.numel(), stream_ptr())
+         C.byref(cfg), ptr(norm_out), param.numel(), stream_ptr(),
+         tag="a2c_clip_optim_step|bytes|%d" % param.numel(),
+         work=(24 if kind == 0 else 32) * param.numel())

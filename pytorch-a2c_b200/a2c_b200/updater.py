@@ -133,10 +133,13 @@ class Updater:
         if try_key(hyps, 'norm_returns', False):
             # a2c/updater.py:89-96 (EMA of mean / unbiased std); rare path, stats on host side
             rets = returns if returns is not None else advs + vals.detach().reshape(-1)
-            s = torch.stack([rets.double().sum(), (rets.double() ** 2).sum()])
-            self._allreduce(s)
-            mean = s[0] / n_global
-            std = ((s[1] - n_global * mean * mean) / (n_global - 1)).clamp_min(0).sqrt()
+            if world > 1:
+                s = torch.stack([rets.double().sum(), (rets.double() ** 2).sum()])
+                self._allreduce(s)
+                mean = s[0] / n_global
+                std = ((s[1] - n_global * mean * mean) / (n_global - 1)).clamp_min(0).sqrt()
+            else:
+                mean, std = rets.mean(), rets.std()
             if self.ret_mean is None:
                 self.ret_mean, self.ret_std = mean.float(), std.float()
             else:

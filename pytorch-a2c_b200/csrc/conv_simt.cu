@@ -66,6 +66,7 @@ struct ConvFwdParams {
   float* Y;                // [N][Cout][OH][OW]
   int N, Cin, Cout, OH, OW, pad, relu;
   int rows, WP, PR, CC;    // band rows, patch pitch, patch rows, cin chunk
+  int CoutP;               // Cout rounded up to 4: pitch of the staged weights
 };
 
 template <int K, int S, int PX, int CTT>
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(512, 1) conv_fwd_kernel(const ConvFwdParams p)
   const int tid = threadIdx.x;
   const int g = tid / pixthreads, pt = tid - g * pixthreads;
   const int row = pt / npg, xg = pt - row * npg;
-  const bool active = (g * CTT < p.Cout) && (oy0 + row < p.OH);
+  const bool active = (g * CTT < p.CoutP) && (oy0 + row < p.OH);
   constexpr int NIN = (PX - 1) * S + K;
   constexpr int NL = (PX == 4) ? (NIN + 3) / 4 : 0;
 
@@ -103,17 +104,17 @@ __global__ void __launch_bounds__(512, 1) conv_fwd_kernel(const ConvFwdParams p)
       const int cc = e / (p.WP * p.PR);
       patch[e] = src_value(p.src, n, c0 + cc, iy_base + rr, col - p.pad);
     }
-    const int w_elems = cc_n * K * K * p.Cout;
+    const int w_elems = cc_n * K * K * p.CoutP;
     for (int e = tid; e < w_elems; e += blockDim.x) {
-      const int co = e % p.Cout;
-      int rest = e / p.Cout;
+      const int co = e % p.CoutP;
+      int rest = e / p.CoutP;
       const int kx = rest % K; rest /= K;
       const int ky = rest % K;
       const int cc = rest / K;
       long long gi;
       if (!p.flipT) gi = (((long long)co * p.Cin + c0 + cc) * K + ky) * K + kx;
       else gi = (((long long)(c0 + cc) * p.Cout + co) * K + (K - 1 - ky)) * K + (K - 1 - kx);
-      Ws[e] = __ldg(p.Wt + gi);
+      Ws[e] = co < p.Cout ? __ldg(p.Wt + gi) : 0.0f;
     }
     __syncthreads();
     if (active) {
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(512, 1) conv_fwd_kernel(const ConvFwdParams p)
           }
 #pragma unroll
           for (int kx = 0; kx < K; ++kx) {
-            const float* wp = Ws + ((size_t)(cc * K + ky) * K + kx) * p.Cout + g * CTT;
+            const float* wp = Ws + ((size_t)(cc * K + ky) * K + kx) * p.CoutP + g * CTT;
 #pragma unroll
             for (int q = 0; q < CTT / 4; ++q) {
               const float4 w = *reinterpret_cast<const float4*>(wp + q * 4);
@@ -185,7 +186,8 @@ static int launch_fwd_t(ConvFwdParams p, int logicalW, cudaStream_t st) {
   constexpr int NIN = (PX - 1) * S + K;
   constexpr int NL = (PX == 4) ? (NIN + 3) / 4 : 0;
   const int npg = p.OW / PX;
-  const int G = cdiv(p.Cout, CTT);
+  p.CoutP = (p.Cout + 3) & ~3;
+  const int G = cdiv(p.CoutP, CTT);
   int rows = 512 / (npg * G);
   if (rows < 1) rows = 1;
   if (rows > p.OH) rows = p.OH;
@@ -198,7 +200,7 @@ static int launch_fwd_t(ConvFwdParams p, int logicalW, cudaStream_t st) {
   WP = (WP + 3) & ~3;
   const int PR = (rows - 1) * S + K;
   int CC = p.Cin;
-  auto smem_for = [&](int cc) { return ((size_t)cc * PR * WP + (size_t)cc * K * K * p.Cout) * sizeof(float); };
+  auto smem_for = [&](int cc) { return ((size_t)cc * PR * WP + (size_t)cc * K * K * p.CoutP) * sizeof(float); };
   while (CC > 1 && smem_for(CC) > 96 * 1024) CC = (CC + 1) / 2;
   const size_t smem = smem_for(CC);
   A2C_ARG_CHECK(smem <= 200 * 1024, "conv: shared memory plan too large (%zu)", smem);
@@ -225,7 +227,7 @@ static int launch_fwd_ks(const ConvFwdParams& p, int logicalW, cudaStream_t st) 
     if (c % 16 == 0) return launch_fwd_t<K, S, 4, 16>(p, logicalW, st);
     if (c % 12 == 0) return launch_fwd_t<K, S, 4, 12>(p, logicalW, st);
     if (c % 8 == 0) return launch_fwd_t<K, S, 4, 8>(p, logicalW, st);
-    return launch_fwd_t<K, S, 4, 4>(p, logicalW, st);
+    return launch_fwd_t<K, S, 4, 4>(p, logicalW, st);   // also covers Cout not a multiple of 4
   }
   if (c % 16 == 0) return launch_fwd_t<K, S, 1, 16>(p, logicalW, st);
   if (c % 12 == 0) return launch_fwd_t<K, S, 1, 12>(p, logicalW, st);
@@ -234,7 +236,6 @@ static int launch_fwd_ks(const ConvFwdParams& p, int logicalW, cudaStream_t st) 
 }
 
 static int launch_fwd(const ConvFwdParams& p, int K, int S, int logicalW, cudaStream_t st) {
-  A2C_ARG_CHECK(p.Cout % 4 == 0, "conv: output channels must be a multiple of 4 (got %d)", p.Cout);
   if (K == 3 && S == 1) return launch_fwd_ks<3, 1>(p, logicalW, st);
   if (K == 3 && S == 2) return launch_fwd_ks<3, 2>(p, logicalW, st);
   if (K == 4 && S == 1) return launch_fwd_ks<4, 1>(p, logicalW, st);
@@ -270,18 +271,23 @@ __global__ void __launch_bounds__(512, 1) conv_wgrad_kernel(const ConvWgParams p
 
   float acc[COT][K * K];
   float bacc[COT];
-#pragma unroll
-  for (int i = 0; i < COT; ++i) {
-    bacc[i] = 0.0f;
-#pragma unroll
-    for (int j = 0; j < K * K; ++j) acc[i][j] = 0.0f;
-  }
+  const int wsize = p.Cout * p.Cin * K * K;
+  // this thread's slots in the partial of (CTA, pixel group): flushed after every
+  // work item so no fp32 chain is longer than one item's pixels
+  float* outp = p.partial + ((size_t)blockIdx.x * p.PG + (active ? pg : 0)) * (wsize + p.Cout);
+  bool first = true;
 
   const long long items = (long long)p.N * p.bands;
   for (long long it = blockIdx.x; it < items; it += gridDim.x) {
     const int n = (int)(it / p.bands), band = (int)(it - (long long)n * p.bands);
     const int oy0 = band * p.rows;
     const int nrows = min(p.rows, p.OH - oy0);
+#pragma unroll
+    for (int i = 0; i < COT; ++i) {
+      bacc[i] = 0.0f;
+#pragma unroll
+      for (int j = 0; j < K * K; ++j) acc[i][j] = 0.0f;
+    }
     __syncthreads();
     // stage masked dY as [row][ox][co]
     const int g_elems = p.Cout * nrows * p.OW;
@@ -336,57 +342,37 @@ __global__ void __launch_bounds__(512, 1) conv_wgrad_kernel(const ConvWgParams p
           }
         if (++ox == p.OW) { ox = 0; ++rr; }
       }
-    }
-  }
-  // reduce over pixel groups through shared memory, then write this CTA's partial
-  __syncthreads();
-  const int wsize = p.Cout * p.Cin * K * K;
-  float* red = sm;   // [PG][pairs][COT*K*K + COT] can exceed smem for big layers -> loop groups
-  const int per = COT * K * K + COT;
-  float* outp = p.partial + (size_t)blockIdx.x * (wsize + p.Cout);
-  for (int gsel = 0; gsel < p.PG; ++gsel) {
-    __syncthreads();
-    if (active && pg == gsel) {
-      float* r = red + (size_t)pr * per;
-      if (gsel == 0) {
 #pragma unroll
-        for (int i = 0; i < COT; ++i) {
+      for (int i = 0; i < COT; ++i) {
+        const int co = cog * COT + i;
+        float* o = outp + ((size_t)co * p.Cin + ci) * K * K;
 #pragma unroll
-          for (int j = 0; j < K * K; ++j) r[i * K * K + j] = acc[i][j];
-          r[COT * K * K + i] = bacc[i];
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < COT; ++i) {
-#pragma unroll
-          for (int j = 0; j < K * K; ++j) r[i * K * K + j] += acc[i][j];
-          r[COT * K * K + i] += bacc[i];
-        }
+        for (int j = 0; j < K * K; ++j) o[j] = first ? acc[i][j] : o[j] + acc[i][j];
+        if (ci == 0) outp[wsize + co] = first ? bacc[i] : outp[wsize + co] + bacc[i];
       }
-    }
-  }
-  __syncthreads();
-  if (active && pg == 0) {
-    const float* r = red + (size_t)pr * per;
-#pragma unroll
-    for (int i = 0; i < COT; ++i) {
-      const int co = cog * COT + i;
-#pragma unroll
-      for (int j = 0; j < K * K; ++j) outp[((size_t)co * p.Cin + ci) * K * K + j] = r[i * K * K + j];
-      if (ci == 0) outp[wsize + co] = r[COT * K * K + i];
+      first = false;
     }
   }
 }
 
+// Sums the per-(CTA, pixel group) partials in double.  block = (32 elements, 8 part stripes).
 __global__ void __launch_bounds__(256)
 partial_reduce_kernel(const float* __restrict__ partial, int nparts, int wsize, int cout,
                       float* __restrict__ dW, float* __restrict__ dbias) {
+  __shared__ double sm[8][33];
   const int total = wsize + cout;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    float s = 0.0f;
-    for (int k = 0; k < nparts; ++k) s += partial[(size_t)k * total + e];
-    if (e < wsize) dW[e] = s;
-    else if (dbias) dbias[e - wsize] = s;
+  const int e = blockIdx.x * 32 + threadIdx.x;
+  double s = 0.0;
+  if (e < total)
+    for (int k = threadIdx.y; k < nparts; k += 8) s += (double)partial[(size_t)k * total + e];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && e < total) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    if (e < wsize) dW[e] = (float)t;
+    else if (dbias) dbias[e - wsize] = (float)t;
   }
 }
 
@@ -411,9 +397,7 @@ static int plan_wgrad(const a2c_conv_shape* s, WgPlan* pl) {
   int rows = s->OH;
   auto smem_for = [&](int r) {
     const int PR = (r - 1) * S + K;
-    size_t a = ((size_t)r * s->OW * pl->CoutP + (size_t)s->Cin * PR * pl->WP) * sizeof(float);
-    size_t red = (size_t)pl->pairs * (pl->COT * K * K + pl->COT) * sizeof(float);
-    return a > red ? a : red;
+    return ((size_t)r * s->OW * pl->CoutP + (size_t)s->Cin * PR * pl->WP) * sizeof(float);
   };
   while (rows > 1 && smem_for(rows) > 100 * 1024) rows = (rows + 1) / 2;
   pl->bands = cdiv(s->OH, rows);
@@ -441,7 +425,8 @@ static int launch_wgrad_t(ConvWgParams p, const WgPlan& pl, int wsize, float* dW
   g_launches++;
   A2C_LAUNCH_CHECK();
   const int total = wsize + p.Cout;
-  partial_reduce_kernel<<<cdiv(total, 256), 256, 0, st>>>(p.partial, grid, wsize, p.Cout, dW, dbias);
+  partial_reduce_kernel<<<cdiv(total, 32), dim3(32, 8), 0, st>>>(p.partial, grid * pl.PG, wsize, p.Cout,
+                                                             dW, dbias);
   g_launches++;
   A2C_LAUNCH_CHECK();
   return 0;
@@ -509,7 +494,10 @@ int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, fl
 
 long long a2c_conv2d_bwd_weight_workspace(const a2c_conv_shape* s) {
   if (!s) return 0;
-  return (long long)(num_sms() * 2) * ((long long)s->Cout * s->Cin * s->K * s->K + s->Cout) * sizeof(float);
+  WgPlan pl;
+  if (plan_wgrad(s, &pl)) return 0;
+  return (long long)pl.grid * pl.PG * ((long long)s->Cout * s->Cin * s->K * s->K + s->Cout) *
+         (long long)sizeof(float);
 }
 
 int a2c_conv2d_bwd_weight(const float* X, const a2c_state_view* xview, const float* dY,

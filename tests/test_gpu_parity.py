@@ -376,6 +376,9 @@ def test_state_dict_keys_match_reference_names(dev):
     assert models.get_model_class("conv") is models.ConvModel
 
 
+# magnitude of one optimizer step per element (first steps of RMSprop / Adam are sign-like)
+STEP_SCALE = {"RMSprop": lambda lr: lr / np.sqrt(1 - 0.99), "Adam": lambda lr: lr}
+
 SMALL = [("c1_fc.npz", "FCModel", 4, 15, 2, 256),
          ("small_a3c.npz", "A3CModel", 3, 6, 2, 64),
          ("small_conv.npz", "ConvModel", 3, 6, 2, 32),
@@ -419,21 +422,48 @@ def test_runner_and_updater_against_reference_golden(dev, fname, model, R, T, fs
         shared["states"] = datas["states"]
         if "h_states" in datas:
             shared["h_states"] = torch.from_numpy(g[pre + "h_states"]).to(dev)
+        # float64 evaluation of the same update at the parameters the GPU holds now:
+        # the yardstick for tensors whose fp32 value is ill-conditioned (see the
+        # full-size test below for the rationale of the max(1e-5, 4x reference) bar)
+        cur = {n_: p.detach().cpu().double() for n_, p in net.named_parameters()
+               if n_ in O.param_shapes(model, fs, h)}
+        o64 = O.UpdaterOracle(model, cur, hyps, dtype=torch.float64)
+        o64.ret_mean, o64.ret_std = upd.ret_mean, upd.ret_std
+        if o64.ret_mean is not None:
+            o64.ret_mean, o64.ret_std = o64.ret_mean.cpu().double(), o64.ret_std.cpu().double()
+        sh64 = {key: v.cpu() for key, v in shared.items() if torch.is_tensor(v)}
+        want64 = o64.compute(sh64)["grads"]
         res = upd.compute_gradients(shared)
         grads = {name: p.grad.detach().clone() for name, p in net.named_parameters()}
+        scale = H.golden_grad_scale(g, pre + "grad/")
         for name in O.param_shapes(model, fs, h):
             key = pre + "grad/" + name
             if key in g:
-                assert H.compact_err(grads[name].cpu().numpy(), g[key]) < TOL, name
+                mine = grads[name].cpu().numpy()
+                w64 = H.compact(want64[name].numpy().astype(np.float32)) if want64[name].numel() > H.SAMPLE \
+                    else want64[name].numpy().reshape(-1)
+                ref_own = H.grad_err_compact(g[key], w64, scale)
+                e64 = H.grad_err(mine, w64, scale)
+                assert e64 <= max(TOL, 4 * ref_own), ("grad", k, name, e64, ref_own)
+                eref = H.grad_err(mine, g[key], scale)
+                assert eref <= TOL + 6 * ref_own, ("grad vs fp32 reference", k, name, eref, ref_own)
+        # the flat buffer the optimizer reads is exactly these gradients
+        flat_norm = float(torch.sqrt(sum((gr.double() ** 2).sum() for gr in grads.values())))
+        assert abs(float(upd.flat.grad.double().norm()) - flat_norm) <= 1e-9 * max(1.0, flat_norm)
         upd._optim_step()
         terms = res["loss_terms"].tolist()
         for i, key in enumerate(("Loss", "Pi_Loss", "ValLoss", "Entropy")):
             assert abs(terms[i] - float(g[pre + key])) <= TOL * max(1.0, abs(float(g[pre + key]))), key
-        assert abs(upd.flat.norm.item() - float(g[pre + "GradNorm"])) <= TOL * max(1.0, float(g[pre + "GradNorm"]))
+        # GradNorm: against the float64 norm of the reference's own gradients; the
+        # value the reference reports carries its fp32 norm error (see helpers)
+        true_norm = H.golden_true_norm(g, pre + "grad/")
+        assert abs(upd.flat.norm.item() - true_norm) <= TOL * max(1.0, true_norm)
+        assert abs(upd.flat.norm.item() - float(g[pre + "GradNorm"])) <= 5e-4 * max(1.0, true_norm)
         params = dict(net.named_parameters())
+        step = STEP_SCALE[hyps["optim_type"]](hyps["lr"])
         for name in O.param_shapes(model, fs, h):
-            assert H.compact_err(params[name].detach().cpu().numpy(),
-                             g[pre + "param_after/" + name]) < TOL, name
+            assert H.param_err_ok(params[name].detach().cpu().numpy(),
+                                  g[pre + "param_after/" + name], step), ("param_after", k, name)
 
 
 def test_updater_accepts_reference_layout_fp32_states(dev):
@@ -457,9 +487,10 @@ def test_updater_accepts_reference_layout_fp32_states(dev):
     for key in ("Loss", "Pi_Loss", "ValLoss", "Entropy"):
         assert abs(info[key] - float(g["u0_" + key])) <= TOL * max(1.0, abs(float(g["u0_" + key])))
     params = dict(net.named_parameters())
+    step = STEP_SCALE[hyps["optim_type"]](hyps["lr"])
     for name in O.param_shapes("ConvModel", fs, h):
-        assert H.compact_err(params[name].detach().cpu().numpy(),
-                         g["u0_param_after/" + name]) < TOL, name
+        assert H.param_err_ok(params[name].detach().cpu().numpy(),
+                              g["u0_param_after/" + name], step), name
 
 
 FULL = [("full_c3_a3c.npz", "A3CModel", 1024, 20), ("full_c4_gru_bptt.npz", "GRUModel", 512, 32),
@@ -497,19 +528,64 @@ def test_full_size_update_against_reference_golden(dev, fname, model, R, T):
     upd = updater_mod.Updater(net, hyps)
     res = upd.compute_gradients(shared)
     grads = {name: p.grad.detach().clone() for name, p in net.named_parameters()}
+    scale = H.golden_grad_scale(g, "grad/")
+    # At these sizes (reductions over up to 3e7 cancelling terms) the fp32 CPU
+    # reference is itself 5e-5 .. 1.4e-3 away from the exact gradient for the conv
+    # / first-GEMM parameters (tests/golden/make_fp64.py measures it per tensor and
+    # stores the float64 evaluation).  No fp32 implementation with a different
+    # summation order can sit within 1e-5 of such a value, so the bar is:
+    #   distance(cuda, float64 oracle) <= max(1e-5, 4 * distance(reference fp32, float64 oracle))
+    # i.e. 1e-5 wherever the reference itself achieves it, and the same order as the
+    # reference's own rounding error elsewhere (both are random draws of the same fp32
+    # noise, so a small multiple, not 1x, is the meaningful bound); the distance to the
+    # reference's fp32 output then follows from the triangle inequality (asserted).
+    g64 = H.load(fname.replace("full_", "fp64_"))
     for name in O.param_shapes(model, fs, h):
         key = "grad/" + name
-        if key in g:
-            assert H.compact_err(grads[name].cpu().numpy(), g[key]) < TOL, name
+        if key not in g:
+            continue
+        mine = grads[name].cpu().numpy()
+        ref_own = H.grad_err_compact(g[key], g64["grad64/" + name], scale)
+        e64 = H.grad_err(mine, g64["grad64/" + name], scale)
+        assert e64 <= max(TOL, 4 * ref_own), (name, "vs float64 oracle", e64, "reference's own", ref_own)
+        eref = H.grad_err(mine, g[key], scale)
+        assert eref <= TOL + 6 * ref_own, (name, "vs fp32 reference", eref, ref_own)
     upd._optim_step()
     terms = res["loss_terms"].tolist()
     for i, key in enumerate(("Loss", "Pi_Loss", "ValLoss", "Entropy")):
         assert abs(terms[i] - float(g[key])) <= TOL * max(1.0, abs(float(g[key]))), key
-    assert abs(upd.flat.norm.item() - float(g["GradNorm"])) <= TOL * max(1.0, float(g["GradNorm"]))
+    true_norm = float(g64["norm64"])
+    assert abs(upd.flat.norm.item() - true_norm) <= TOL * max(1.0, true_norm)
+    assert abs(upd.flat.norm.item() - float(g["GradNorm"])) <= 5e-4 * max(1.0, true_norm)
     params = dict(net.named_parameters())
+    step = STEP_SCALE[hyps["optim_type"]](hyps["lr"])
     for name in O.param_shapes(model, fs, h):
-        assert H.compact_err(params[name].detach().cpu().numpy(),
-                         g["param_after/" + name]) < TOL, name
+        assert H.param_err_ok(params[name].detach().cpu().numpy(), g["param_after/" + name], step), name
+
+
+@pytest.mark.parametrize("kind", ["RMSprop", "Adam"])
+def test_fused_clip_optimizer_matches_torch(dev, kind):
+    """clip_grad_norm_ + optimizer.step + zero_grad over the flat buffer vs
+    torch.optim on the CPU with identical gradients, three steps."""
+    from a2c_b200 import models, updater as updater_mod
+    hyps = dict(is_discrete=True, lr=1e-3, optim_type=kind, max_norm=0.5)
+    net = models.FCModel([2, 80, 80], 3, h_size=16).to(dev)
+    ref = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.named_parameters()}
+    opt = getattr(torch.optim, kind)(list(ref.values()), lr=1e-3)
+    upd = updater_mod.Updater(net, hyps)
+    gen = torch.Generator().manual_seed(0)
+    for it in range(3):
+        for k, p in net.named_parameters():
+            gr = torch.randn(p.shape, generator=gen) * (0.001 if it == 1 else 1.0)
+            p.grad.copy_(gr.to(dev))
+            ref[k].grad = gr.clone()
+        norm = torch.nn.utils.clip_grad_norm_(list(ref.values()), 0.5)
+        opt.step()
+        upd._optim_step()
+        assert abs(upd.flat.norm.item() - float(norm)) <= 1e-5 * float(norm)
+        assert float(upd.flat.grad.abs().max()) == 0.0               # zero_grad
+        for k, p in net.named_parameters():
+            assert H.rel_err(p.detach().cpu().numpy(), ref[k].detach().numpy()) < 5e-6, (it, k)
 
 
 def test_launches_come_from_our_library(dev):
