@@ -253,7 +253,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {0: "f32", 1: "f32 (3xTF32 tcgen05, fp32 accumulate)", 2: "bf16"}[args.precision],
+        "dtype": {0: "f32 (FFMA)", 1: "f32 (GEMMs: 3xTF32 split on tcgen05, fp32 accumulate; convs: FFMA)",
+                  2: "tf32 (single pass)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": desc, "model": model, "n_envs_per_gpu": R, "n_tsteps": T,
                    "transitions_per_step": N * world, "parallelism": "env-sharded dp%d" % world,
@@ -423,7 +424,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", type=int, default=int(os.environ.get("A2C_PRECISION", "0")))
+    ap.add_argument("--precision", type=int, default=int(os.environ.get("A2C_PRECISION", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

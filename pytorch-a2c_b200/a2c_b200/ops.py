@@ -13,8 +13,10 @@ from ._lib import ConvShape, LossCfg, OptimCfg, StateView, call, ptr, require_cu
 
 PLANE = 6400
 
-# 0 = fp32 FFMA (exact-parity path), 1 = 3xTF32 tcgen05, 2 = bf16 tcgen05 (stated tolerance)
-_PRECISION = 0
+# GEMM / conv contraction mode: 0 = fp32 FFMA, 1 = 3xTF32 on tcgen05 (fp32 parity, the
+# default), 2 = single-pass TF32 on tcgen05 (stated tolerance 2e-3).  A2C_PRECISION overrides.
+import os as _os
+_PRECISION = int(_os.environ.get("A2C_PRECISION", "1"))
 
 
 def set_precision(p):

@@ -258,6 +258,40 @@ def test_gemm_fp32(dev, M, N, K, ta, tb):
     assert H.rel_err(got2.cpu().numpy(), want2.numpy()) < TOL
 
 
+@pytest.mark.parametrize("M,N,K,ta,tb", [
+    (128, 128, 64, False, True), (256, 256, 512, False, False), (640, 2000, 2560, False, True),
+    (512, 1280, 2000, False, False), (2000, 2560, 640, True, False), (300, 200, 100, True, True),
+    (4096, 256, 2048, False, True), (5120, 32, 256, False, True), (130, 260, 132, False, True),
+    (256, 128, 25600, False, True)])
+@pytest.mark.parametrize("precision,tol", [(1, 1e-5), (2, 2e-3)])
+def test_gemm_tcgen05(dev, M, N, K, ta, tb, precision, tol):
+    """tcgen05 path of a2c_gemm: 3xTF32 (fp32-parity mode, 1e-5) and single-pass
+    TF32 (2e-3), every operand layout, ragged edges, long K (accumulation)."""
+    ops = ops_mod()
+    gen = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn((K, M) if ta else (M, K), generator=gen)
+    B = torch.randn((N, K) if tb else (K, N), generator=gen)
+    bias = torch.randn(N, generator=gen)
+    Am = A.t() if ta else A
+    Bm = B.t() if tb else B
+    want = (Am.double() @ Bm.double() + bias.double()).clamp_min(0)
+    sam, sak = (1, M) if ta else (K, 1)
+    sbk, sbn = (1, K) if tb else (N, 1)
+    from a2c_b200 import _lib
+    n0 = _lib.launch_count()
+    got = ops.gemm(A.to(dev), sam, sak, B.to(dev), sbk, sbn, M, N, K, bias=bias.to(dev), relu=True,
+                   precision=precision)
+    assert _lib.launch_count() == n0 + 1
+    # error relative to the scale of the products being summed (sqrt(K) for N(0,1) operands)
+    err = (got.cpu().double() - want).abs().max().item() / max(want.abs().max().item(), 1e-30)
+    assert err < tol, err
+    got2 = ops.gemm(A.to(dev), sam, sak, B.to(dev), sbk, sbn, M, N, K, out=got.clone(), ldc=N, beta=1,
+                    precision=precision)
+    want2 = want + Am.double() @ Bm.double()
+    err2 = (got2.cpu().double() - want2).abs().max().item() / max(want2.abs().max().item(), 1e-30)
+    assert err2 < tol, err2
+
+
 CONVS = [  # Cin, Cout, H, K, stride, pad  -- every layer shape of the four models
     (2, 16, 80, 3, 1, 1), (16, 24, 80, 3, 1, 1), (24, 32, 80, 3, 2, 1), (32, 64, 40, 3, 2, 1),
     (16, 24, 80, 3, 2, 1), (24, 32, 40, 3, 2, 1), (32, 48, 20, 3, 2, 1), (48, 64, 10, 3, 2, 1),
