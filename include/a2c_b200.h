@@ -168,21 +168,25 @@ typedef struct {
 } a2c_conv_shape;
 
 /* Y = relu?(conv2d(X, Wt) + bias).  X f32 [N, Cin, H, W], or a state view when
- * xview != NULL (then X is ignored and N = R*view.T).  Wt f32 [Cout, Cin, K, K]. */
+ * xview != NULL (then X is ignored and N = R*view.T).  Wt f32 [Cout, Cin, K, K].
+ * precision (all three conv entry points): 0 = fp32 FFMA direct convolution;
+ * 1 = implicit GEMM on tcgen05 with the 3xTF32 split (fp32 parity); 2 = single-pass
+ * TF32.  The tensor-core backward kernels need dY already ReLU-masked (Ymask NULL,
+ * see a2c_relu_bwd); with a non-NULL Ymask they run the FFMA kernels. */
 int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
                    const float* bias, float* Y, int N, const a2c_conv_shape* s, int relu,
-                   void* stream);
+                   int precision, void* stream);
 /* dX = conv2d_transpose(dY * (Ymask > 0)).  Ymask (may be NULL) is the forward
  * output whose ReLU gates dY. */
 int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
-                        const a2c_conv_shape* s, void* stream);
+                        const a2c_conv_shape* s, int precision, void* stream);
 /* dW, dbias from X (or xview) and dY * (Ymask > 0).  workspace >=
  * a2c_conv2d_bwd_weight_workspace(s) bytes. */
 long long a2c_conv2d_bwd_weight_workspace(const a2c_conv_shape* s);
 int a2c_conv2d_bwd_weight(const float* X, const a2c_state_view* xview, const float* dY,
                           const float* Ymask, float* dW, float* dbias, int N,
                           const a2c_conv_shape* s, void* workspace, long long workspace_bytes,
-                          void* stream);
+                          int precision, void* stream);
 
 /* LayerNorm over the last dim (eps 1e-5), rows x H.  Saves mean / rstd f32 [rows]. */
 int a2c_layernorm_fwd(const float* X, const float* gamma, const float* beta, float* Y,

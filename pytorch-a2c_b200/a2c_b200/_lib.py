@@ -62,10 +62,10 @@ SIGNATURES = {
     "a2c_linear_state_wgrad": [_SV, _p, _p, _i, _i, _p, _ll, _p],
     "a2c_colsum": [_p, _p, _ll, _i, _p],
     "a2c_relu_bwd": [_p, _p, _p, _ll, _p],
-    "a2c_conv2d_fwd": [_p, _SV, _p, _p, _p, _i, _CS, _i, _p],
-    "a2c_conv2d_bwd_data": [_p, _p, _p, _p, _i, _CS, _p],
+    "a2c_conv2d_fwd": [_p, _SV, _p, _p, _p, _i, _CS, _i, _i, _p],
+    "a2c_conv2d_bwd_data": [_p, _p, _p, _p, _i, _CS, _i, _p],
     "a2c_conv2d_bwd_weight_workspace": [_CS],
-    "a2c_conv2d_bwd_weight": [_p, _SV, _p, _p, _p, _p, _i, _CS, _p, _ll, _p],
+    "a2c_conv2d_bwd_weight": [_p, _SV, _p, _p, _p, _p, _i, _CS, _p, _ll, _i, _p],
     "a2c_layernorm_fwd": [_p, _p, _p, _p, _p, _p, _ll, _i, _p],
     "a2c_layernorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _p],
     "a2c_gru_gates1": [_p, _p, _p, _p, _p, _p, _ll, _i, _p],

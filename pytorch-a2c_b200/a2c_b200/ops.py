@@ -319,9 +319,9 @@ class Conv2dFn(torch.autograd.Function):
         flops = 2.0 * N * s.OH * s.OW * Cout * Cin * K * K
         sig = "%d:%d>%d,%dx%d,k%ds%d" % (N, Cin, Cout, H, Wd, K, stride)
         call("a2c_conv2d_fwd", None if is_view else ptr(x), C.byref(x.c) if is_view else None,
-             ptr(W), ptr(b), ptr(y), N, C.byref(s), 1 if relu else 0, stream_ptr(),
+             ptr(W), ptr(b), ptr(y), N, C.byref(s), 1 if relu else 0, _PRECISION, stream_ptr(),
              tag="a2c_conv2d_fwd|flops|" + sig, work=flops)
-        ctx.flops, ctx.sig = flops, sig
+        ctx.flops, ctx.sig, ctx.precision = flops, sig, _PRECISION
         ctx.shape, ctx.relu, ctx.is_view, ctx.N = s, relu, is_view, N
         if is_view:
             ctx.view = x
@@ -340,10 +340,14 @@ class Conv2dFn(torch.autograd.Function):
             W, y, x = ctx.saved_tensors
         dy = dy.contiguous()
         mask = y if ctx.relu else None
+        prec = ctx.precision
+        if prec != 0 and mask is not None:
+            dy = relu_bwd(dy, y)       # the tensor-core kernels take the masked gradient
+            mask = None
         dx = dW = db = None
         if not ctx.is_view and ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            call("a2c_conv2d_bwd_data", ptr(dy), ptr(mask), ptr(W), ptr(dx), N, C.byref(s),
+            call("a2c_conv2d_bwd_data", ptr(dy), ptr(mask), ptr(W), ptr(dx), N, C.byref(s), prec,
                  stream_ptr(), tag="a2c_conv2d_bwd_data|flops|" + ctx.sig, work=ctx.flops)
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
             dW = torch.empty_like(W)
@@ -351,7 +355,7 @@ class Conv2dFn(torch.autograd.Function):
             need = call("a2c_conv2d_bwd_weight_workspace", C.byref(s))
             ws = workspace(W.device, max(need, 64 << 20))
             call("a2c_conv2d_bwd_weight", ptr(x), C.byref(ctx.view.c) if ctx.is_view else None,
-                 ptr(dy), ptr(mask), ptr(dW), ptr(db), N, C.byref(s), ptr(ws), ws.numel(),
+                 ptr(dy), ptr(mask), ptr(dW), ptr(db), N, C.byref(s), ptr(ws), ws.numel(), prec,
                  stream_ptr(), tag="a2c_conv2d_bwd_weight|flops|" + ctx.sig, work=ctx.flops)
         return dx, dW, db, None, None, None
 

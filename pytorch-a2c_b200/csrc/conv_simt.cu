@@ -456,6 +456,16 @@ static int fill_src(ConvSrc* src, const float* X, const a2c_state_view* xview, c
   return 0;
 }
 
+// conv_tc.cu: 0 = ran on the tensor cores, 1 = shape not handled, else error
+int conv_fwd_tc_try(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias,
+                    float* Y, int N, const a2c_conv_shape* s, int relu, int precision, cudaStream_t st);
+int conv_dgrad_tc_try(const float* dY, const float* Wt, float* dX, int N, const a2c_conv_shape* s,
+                      int precision, cudaStream_t st);
+long long conv_wgrad_tc_workspace(const a2c_conv_shape* s);
+int conv_wgrad_tc_try(const float* X, const a2c_state_view* xview, const float* dY, float* dW,
+                      float* dbias, int N, const a2c_conv_shape* s, void* workspace,
+                      long long workspace_bytes, int precision, cudaStream_t st);
+
 }  // namespace a2c
 
 using namespace a2c;
@@ -463,10 +473,15 @@ using namespace a2c;
 extern "C" {
 
 int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias,
-                   float* Y, int N, const a2c_conv_shape* s, int relu, void* stream) {
+                   float* Y, int N, const a2c_conv_shape* s, int relu, int precision, void* stream) {
   if (int rc = check_shape(s)) return rc;
   A2C_ARG_CHECK(Wt && Y && N >= 0, "conv_fwd: bad args");
   if (N == 0) return 0;
+  if (precision != 0) {
+    A2C_ARG_CHECK(xview || X, "conv_fwd: null input");
+    int rc = conv_fwd_tc_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
+    if (rc != 1) return rc;
+  }
   ConvFwdParams p{};
   if (int rc = fill_src(&p.src, X, xview, s)) return rc;
   p.Wt = Wt; p.flipT = 0; p.bias = bias; p.Y = Y; p.N = N; p.Cin = s->Cin; p.Cout = s->Cout;
@@ -475,10 +490,14 @@ int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
 }
 
 int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
-                        const a2c_conv_shape* s, void* stream) {
+                        const a2c_conv_shape* s, int precision, void* stream) {
   if (int rc = check_shape(s)) return rc;
   A2C_ARG_CHECK(dY && Wt && dX && N >= 0, "conv_bwd_data: bad args");
   if (N == 0) return 0;
+  if (precision != 0 && !Ymask) {
+    int rc = conv_dgrad_tc_try(dY, Wt, dX, N, s, precision, as_stream(stream));
+    if (rc != 1) return rc;
+  }
   // dX = stride-1 conv of the dilated, masked dY with flipped/transposed weights
   ConvFwdParams p{};
   p.src.X = dY; p.src.mask = Ymask; p.src.SC = s->Cout; p.src.SH = s->OH; p.src.SW = s->OW;
@@ -496,14 +515,16 @@ long long a2c_conv2d_bwd_weight_workspace(const a2c_conv_shape* s) {
   if (!s) return 0;
   WgPlan pl;
   if (plan_wgrad(s, &pl)) return 0;
-  return (long long)pl.grid * pl.PG * ((long long)s->Cout * s->Cin * s->K * s->K + s->Cout) *
-         (long long)sizeof(float);
+  const long long simt = (long long)pl.grid * pl.PG *
+                         ((long long)s->Cout * s->Cin * s->K * s->K + s->Cout) * (long long)sizeof(float);
+  const long long tcw = conv_wgrad_tc_workspace(s);
+  return simt > tcw ? simt : tcw;
 }
 
 int a2c_conv2d_bwd_weight(const float* X, const a2c_state_view* xview, const float* dY,
                           const float* Ymask, float* dW, float* dbias, int N,
                           const a2c_conv_shape* s, void* workspace, long long workspace_bytes,
-                          void* stream) {
+                          int precision, void* stream) {
   if (int rc = check_shape(s)) return rc;
   A2C_ARG_CHECK(dY && dW && N >= 0, "conv_bwd_weight: bad args");
   A2C_ARG_CHECK(workspace && workspace_bytes >= a2c_conv2d_bwd_weight_workspace(s),
@@ -514,6 +535,11 @@ int a2c_conv2d_bwd_weight(const float* X, const a2c_state_view* xview, const flo
     A2C_CUDA_CHECK(cudaMemsetAsync(dW, 0, sizeof(float) * wsize, st));
     if (dbias) A2C_CUDA_CHECK(cudaMemsetAsync(dbias, 0, sizeof(float) * s->Cout, st));
     return 0;
+  }
+  if (precision != 0 && !Ymask) {
+    A2C_ARG_CHECK(xview || X, "conv_bwd_weight: null input");
+    int rc = conv_wgrad_tc_try(X, xview, dY, dW, dbias, N, s, workspace, workspace_bytes, precision, st);
+    if (rc != 1) return rc;
   }
   WgPlan pl;
   if (plan_wgrad(s, &pl)) {

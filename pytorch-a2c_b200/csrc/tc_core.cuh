@@ -1,0 +1,301 @@
+// tcgen05 tile engine shared by the dense GEMM and the implicit-GEMM convolutions.
+//
+// One CTA computes a 128 x BN fp32 tile  D = sum_k A[m,k] * B[n,k]  on the 5th-gen
+// tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM):
+//   warps 0-3   producers of the A tile   (Problem::produce_a)
+//   warps 4-7   producers of the B tile   (Problem::produce_b)
+//   warps 8-15  accumulator drain + epilogue (Problem::epilogue)
+//   warp  16    MMA issuer (one elected lane), warp 17 TMEM allocator
+// Operand tiles live in shared memory in the canonical K-major SWIZZLE_128B UMMA
+// layout: rows of 32 fp32 (128 B), 16-byte chunk index XOR (row & 7), 8-row
+// groups 1024 B apart.  Producers are ordinary threads, so a Problem can gather
+// (im2col, transposed, masked, u8 -> f32) while it fills the tile -- no operand
+// is ever materialised in HBM in a tensor-core friendly layout.
+//
+// SPLIT3 (3xTF32): hi = rna_tf32(x), lo = x - hi;  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
+// The TMEM accumulator adds with truncation (measured on B200: error grows
+// linearly with the number of chained MMAs, 2e-4 at K = 25600), so K is consumed
+// in chunks of KC k-blocks into two ping-pong TMEM accumulators and the drain
+// warps add every finished chunk into fp32 registers with round-to-nearest
+// while the tensor core works on the next chunk: 1e-5 of fp64 at any K.
+#pragma once
+#include "common.cuh"
+
+namespace a2c {
+namespace tc {
+
+constexpr int TM = 128;            // UMMA M (cta_group::1)
+constexpr int KB = 32;             // k-block: 32 fp32 = one 128-byte swizzle row
+constexpr int PROD_THREADS = 128;  // per operand
+constexpr int THREADS = 576;       // 18 warps
+constexpr int NUM_PROD_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int KC = 8;              // k-blocks per TMEM accumulation chunk (256 k)
+constexpr int SCRATCH_BYTES = 4096;  // per-CTA scratch handed to Problem::init
+
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused for SW128 K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+// kind::tf32, fp32 accumulate, both operands K-major (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ int swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+// Stores one 16-byte chunk (4 consecutive k of one row) into the swizzled tile(s).
+template <bool SPLIT3>
+__device__ __forceinline__ void store_chunk(uint8_t* hi_tile, uint8_t* lo_tile, int row, int chunk,
+                                            float4 v) {
+  const int off = swz(row, chunk);
+  if constexpr (SPLIT3) {
+    float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+    *reinterpret_cast<float4*>(hi_tile + off) = h;
+    *reinterpret_cast<float4*>(lo_tile + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  } else {
+    *reinterpret_cast<float4*>(hi_tile + off) = v;
+  }
+}
+
+// Stores one element (row, k) into the swizzled tile(s).
+template <bool SPLIT3>
+__device__ __forceinline__ void store_elem(uint8_t* hi_tile, uint8_t* lo_tile, int row, int k, float v) {
+  const int off = swz(row, k >> 2) + ((k & 3) << 2);
+  if constexpr (SPLIT3) {
+    const float h = tf32_rna(v);
+    *reinterpret_cast<float*>(hi_tile + off) = h;
+    *reinterpret_cast<float*>(lo_tile + off) = v - h;
+  } else {
+    *reinterpret_cast<float*>(hi_tile + off) = v;
+  }
+}
+
+// Problem concept:
+//   struct Params { ...; int nkb; int kb_per_split; };        (nkb = total k-blocks)
+//   static __device__ void init(const Params&, uint8_t* scratch, int tid);      all threads, before the main loop
+//   static __device__ void produce_a(const Params&, const uint8_t* scratch, int m0, int kb, uint8_t* hi, uint8_t* lo, int t);
+//   static __device__ void produce_b(const Params&, const uint8_t* scratch, int n0, int kb, uint8_t* hi, uint8_t* lo, int t);
+//   static __device__ void epilogue(const Params&, int m, int n_begin, const float* acc, int count, int split);
+template <int BN, bool SPLIT3, class P>
+__global__ void __launch_bounds__(THREADS, 1) tc_kernel(const typename P::Params p, int stages, int mtiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int A_BYTES = TM * 128, B_BYTES = BN * 128;
+  constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  constexpr int HALF = BN / 2;      // columns per drain warp
+  // 1024-byte alignment of every tile is required by SWIZZLE_128B
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* scratch = smem + stages * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(scratch + SCRATCH_BYTES);
+  uint64_t* empty = full + stages;
+  uint64_t* acc_full = empty + stages;       // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  // persistent over m tiles: this CTA owns tiles blockIdx.y, blockIdx.y + gridDim.y, ...
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(p.nkb, kb_begin + p.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+  const int nchunks = (nkb + KC - 1) / KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], NUM_PROD_WARPS);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], NUM_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 17) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)(2 * BN)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  P::init(p, scratch, threadIdx.x);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto stage_ptr = [&](int s) { return smem + s * STAGE_BYTES; };
+  // stage layout: [A_hi][A_lo?][B_hi][B_lo?]
+  if (warp < NUM_PROD_WARPS) {
+    const bool isA = warp < 4;
+    const int t = threadIdx.x & (PROD_THREADS - 1);
+    int it = 0;
+    for (int mt = blockIdx.y; mt < mtiles; mt += gridDim.y) {
+      const int m0 = mt * TM;
+      for (int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % stages;
+        const uint32_t parity = (it / stages) & 1;
+        mbar_wait(&empty[s], parity ^ 1);
+        uint8_t* st = stage_ptr(s);
+        if (isA) {
+          P::produce_a(p, scratch, m0, kb_begin + i, st, st + A_BYTES, t);
+        } else {
+          uint8_t* b = st + (SPLIT3 ? 2 : 1) * A_BYTES;
+          P::produce_b(p, scratch, n0, kb_begin + i, b, b + B_BYTES, t);
+        }
+        fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+      }
+    }
+  } else if (warp == 16) {
+    constexpr uint32_t idesc = make_idesc(BN);
+    int it = 0, gchunk0 = 0;
+    for (int mt = blockIdx.y; mt < mtiles; mt += gridDim.y, gchunk0 += nchunks)
+    for (int i = 0; i < nkb; ++i, ++it) {
+      const int s = it % stages;
+      const uint32_t parity = (it / stages) & 1;
+      const int chunk = gchunk0 + i / KC, buf = chunk & 1;
+      if (i % KC == 0) {                        // new chunk: its TMEM buffer must have been drained
+        mbar_wait(&acc_empty[buf], ((chunk >> 1) & 1) ^ 1);
+        tc_fence_after();
+      }
+      mbar_wait(&full[s], parity);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        const uint32_t a_hi = smem_u32(stage_ptr(s));
+        const uint32_t a_lo = a_hi + A_BYTES;
+        const uint32_t b_hi = a_hi + (SPLIT3 ? 2 : 1) * A_BYTES;
+        const uint32_t b_lo = b_hi + B_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < KB / 8; ++kk) {
+          const uint32_t koff = kk * 32;     // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+          const uint32_t first = ((i % KC) | kk) ? 1u : 0u;
+          if constexpr (SPLIT3) {
+            mma_tf32(tmem_d, make_desc(a_lo + koff), make_desc(b_hi + koff), idesc, first);
+            mma_tf32(tmem_d, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1u);
+            mma_tf32(tmem_d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, 1u);
+          } else {
+            mma_tf32(tmem_d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
+          }
+        }
+        mma_commit(&empty[s]);                                   // frees the stage when these MMAs retire
+        if (i % KC == KC - 1 || i == nkb - 1) mma_commit(&acc_full[buf]);   // chunk complete
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 8 && warp < 8 + NUM_EPI_WARPS) {
+    // ---- drain + epilogue: thread <-> accumulator row (TMEM lane), half of the columns ----
+    const int e = warp - 8, q = e & 3, hsel = e >> 2;
+    int gchunk = 0;
+    for (int mt = blockIdx.y; mt < mtiles; mt += gridDim.y) {
+    const int m0 = mt * TM;
+    float acc[HALF];
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) acc[j] = 0.0f;
+    for (int chunk = 0; chunk < nchunks; ++chunk, ++gchunk) {
+      const int buf = gchunk & 1;
+      mbar_wait(&acc_full[buf], (gchunk >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + hsel * HALF;
+#pragma unroll
+      for (int c0 = 0; c0 < HALF; c0 += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+              "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+    P::template epilogue<HALF>(p, m0 + q * 32 + lane, n0 + hsel * HALF, acc, (int)blockIdx.z);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)(2 * BN)));
+  }
+}
+
+template <int BN, bool SPLIT3>
+constexpr int stage_bytes() { return (SPLIT3 ? 2 : 1) * (TM * 128 + BN * 128); }
+
+// Launch helper: grid = (n tiles, m tiles, splits).
+template <int BN, bool SPLIT3, class P>
+int tc_launch(const typename P::Params& p, int mtiles, int ntiles, int splits, cudaStream_t st) {
+  constexpr int SB = stage_bytes<BN, SPLIT3>();
+  int stages = (196 * 1024) / SB;
+  if (stages > 4) stages = 4;
+  if (stages < 2) return 1;
+  const size_t smem = (size_t)stages * SB + 1024 /*align slack*/ + SCRATCH_BYTES + (2 * stages + 4) * 8 + 16;
+  auto kern = tc_kernel<BN, SPLIT3, P>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+    if (e != cudaSuccess) {
+      set_error("tc_launch: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  // one CTA per SM (the tile ring takes most of shared memory): persistent over m tiles
+  int gy = mtiles;
+  const int cap = num_sms() / (ntiles * splits > 0 ? ntiles * splits : 1);
+  if (gy > cap) gy = cap < 1 ? 1 : cap;
+  dim3 grid(ntiles, gy, splits);
+  kern<<<grid, THREADS, smem, st>>>(p, stages, mtiles);
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace a2c
