@@ -3,7 +3,9 @@
 // NCHW fp32 (first layer: also the u8 plane ring of stage 1).  Nothing is
 // im2col'ed in HBM: the producer warps gather the operand tile straight into
 // the swizzled UMMA layout, lanes running along the contiguous pixel dimension
-// so every global load instruction is coalesced.
+// so every global load instruction is coalesced, and all loads of a k-block are
+// issued before the first conversion / shared store (latency is overlapped
+// inside a thread, not only across warps).
 //
 //   forward        D[pixel, co]   = sum_{ci,ky,kx} X[n,ci,oy*s+ky-p,ox*s+kx-p] * W[co,ci,ky,kx]
 //   backward-data  D[inpixel, ci] = sum_{co,ky,kx} dY[n,co,(iy+p-ky)/s,(ix+p-kx)/s] * W[co,ci,ky,kx]
@@ -53,73 +55,112 @@ __device__ __forceinline__ uint32_t view_chanmask(const a2c_state_view& v, long 
   return m;
 }
 
+// Source of the gathered X operand: fp32 NCHW, or the stage-1 state view (u8 / f32).
+struct XRow {
+  const uint8_t* p8;
+  const float* p32;
+  int iy0, ix0;
+  uint32_t cmask;
+  bool ok;
+};
+
+__device__ __forceinline__ void xrow_setup(const ConvParams& p, bool ok, int n, int iy0, int ix0, XRow& r) {
+  r.ok = ok; r.iy0 = iy0; r.ix0 = ix0; r.cmask = 0xffffffffu; r.p8 = nullptr; r.p32 = nullptr;
+  const long long sp = (long long)iy0 * p.W + ix0;
+  if (p.use_view) {
+    const long long rr = n / p.view.T;
+    const int tt = n - (int)rr * p.view.T;
+    const long long base = rr * p.view.stride_r + (long long)tt * p.view.stride_t + sp;
+    r.cmask = view_chanmask(p.view, rr, tt);
+    if (p.view.dtype == 0) r.p8 = static_cast<const uint8_t*>(p.view.base) + base;
+    else r.p32 = static_cast<const float*>(p.view.base) + base;
+  } else {
+    r.p32 = p.src + (long long)n * p.Cin * p.H * p.W + sp;
+  }
+}
+
+__device__ __forceinline__ float xrow_load(const ConvParams& p, const XRow& r, uint32_t e) {
+  const int ky = (e >> 20) & 15, kx = (e >> 24) & 15;
+  const bool ok = r.ok && ((e >> 28) & 1) && (unsigned)(r.iy0 + ky) < (unsigned)p.H &&
+                  (unsigned)(r.ix0 + kx) < (unsigned)p.W && ((r.cmask >> (e >> 29)) & 1);
+  if (!ok) return 0.0f;
+  const int d = (int)(e & 0xFFFFF);
+  return r.p8 ? (float)r.p8[d] : __ldg(r.p32 + d);
+}
+
+template <int NV>
+struct Frag {
+  float v[NV];
+};
+
+// weights tile (B of forward / backward-data): BN x 32; unit u -> row = u % BN, chunk = u / BN so
+// that a quarter-warp stores 8 consecutive rows of one chunk (conflict-free); addr(row, k) by functor
+template <int BN, int NT, class F>
+__device__ __forceinline__ void load_weights(Frag<BN / 4>& f, int t, F addr) {
+#pragma unroll
+  for (int i = 0; i < BN * 8 / NT; ++i) {
+    const int u = i * NT + t, row = u % BN, c = u / BN;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f.v[i * 4 + j] = addr(row, c * 4 + j);
+  }
+}
+template <int BN, bool SPLIT3, int NT>
+__device__ __forceinline__ void store_weights(const Frag<BN / 4>& f, uint8_t* hi, uint8_t* lo, int t) {
+#pragma unroll
+  for (int i = 0; i < BN * 8 / NT; ++i) {
+    const int u = i * NT + t, row = u % BN, c = u / BN;
+    store_chunk<SPLIT3>(hi, lo, row, c, make_float4(f.v[i * 4], f.v[i * 4 + 1], f.v[i * 4 + 2], f.v[i * 4 + 3]));
+  }
+}
+
 // ------------------------------------------------------------------ forward --------
 template <int BN, bool SPLIT3>
 struct ConvFwdProblem {
   using Params = ConvParams;
-  static __device__ __forceinline__ void init(const Params& p, uint8_t* scratch, int tid) {
+  static constexpr int NA = 8, NB = 4, KC = 8;
+  using AState = XRow;
+  static __device__ __forceinline__ void init(const Params& p, uint8_t* scratch, int tid, int nt) {
     uint32_t* tab = reinterpret_cast<uint32_t*>(scratch);
     const int KK = p.K * p.K;
     const int plane = p.use_view ? (int)p.view.stride_c : p.H * p.W;
-    for (int k = tid; k < p.nkb * KB; k += THREADS) {
+    for (int k = tid; k < p.nkb * KB; k += nt) {
       const int ci = k / KK, r = k - ci * KK, ky = r / p.K, kx = r - ky * p.K;
       tab[k] = pack_tap(ci * plane + ky * p.W + kx, ky, kx, k < p.red, ci);
     }
   }
-  static __device__ __forceinline__ void produce_a(const Params& p, const uint8_t* scratch, int m0,
-                                                   int kb, uint8_t* hi, uint8_t* lo, int t) {
-    const uint32_t* tab = reinterpret_cast<const uint32_t*>(scratch) + kb * KB;
-    const long long m = (long long)m0 + t;
-    const bool rowok = m < p.rows;
+  // thread t: row = t & 127 (a pixel), chunks 4*(t>>7) .. +3 of every k-block
+  static __device__ __forceinline__ void a_setup(const Params& p, const uint8_t*, int m0, int t, AState& st) {
+    const long long m = (long long)m0 + (t & 127);
+    const bool ok = m < p.rows;
     const int ohw = p.OH * p.OW;
-    const int n = rowok ? (int)(m / ohw) : 0;
-    const int pix = rowok ? (int)(m - (long long)n * ohw) : 0;
+    const int n = ok ? (int)(m / ohw) : 0;
+    const int pix = ok ? (int)(m - (long long)n * ohw) : 0;
     const int oy = pix / p.OW, ox = pix - oy * p.OW;
-    const int iy0 = oy * p.S - p.P, ix0 = ox * p.S - p.P;
-    long long base;
-    uint32_t cmask = 0xffffffffu;
-    if (p.use_view) {
-      const long long r = n / p.view.T;
-      const int tt = n - (int)r * p.view.T;
-      base = r * p.view.stride_r + (long long)tt * p.view.stride_t + (long long)iy0 * p.W + ix0;
-      cmask = view_chanmask(p.view, r, tt);
-    } else {
-      base = (long long)n * p.Cin * p.H * p.W + (long long)iy0 * p.W + ix0;
-    }
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t e = tab[c * 4 + j];
-        const int ky = (e >> 20) & 15, kx = (e >> 24) & 15;
-        const bool ok = rowok && ((e >> 28) & 1) && (unsigned)(iy0 + ky) < (unsigned)p.H &&
-                        (unsigned)(ix0 + kx) < (unsigned)p.W && ((cmask >> (e >> 29)) & 1);
-        float x = 0.0f;
-        if (ok) {
-          const long long a = base + (e & 0xFFFFF);
-          if (p.use_view && p.view.dtype == 0) x = (float)static_cast<const uint8_t*>(p.view.base)[a];
-          else if (p.use_view) x = static_cast<const float*>(p.view.base)[a];
-          else x = __ldg(p.src + a);
-        }
-        v[j] = x;
-      }
-      store_chunk<SPLIT3>(hi, lo, t, c, make_float4(v[0], v[1], v[2], v[3]));
-    }
+    xrow_setup(p, ok, n, oy * p.S - p.P, ox * p.S - p.P, st);
   }
-  static __device__ __forceinline__ void produce_b(const Params& p, const uint8_t*, int n0, int kb,
-                                                   uint8_t* hi, uint8_t* lo, int t) {
-    // weights: B[co][k] = wt[co*red + k]; lanes run along co so a quarter-warp stores 8 rows x 1 chunk
+  using AFrag = Frag<16>;
+  using BFrag = Frag<BN / 4>;
+  static __device__ __forceinline__ void load_a(const Params& p, const AState& st, const uint8_t* scratch,
+                                                int, int kb, int t, AFrag& f) {
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(scratch) + kb * KB + (t >> 7) * 16;
 #pragma unroll
-    for (int i = 0; i < BN * 8 / PROD_THREADS; ++i) {
-      const int u = i * PROD_THREADS + t, row = u % BN, c = u / BN;
-      const int co = n0 + row, k = kb * KB + c * 4;
-      float v[4];
+    for (int j = 0; j < 16; ++j) f.v[j] = xrow_load(p, st, tab[j]);
+  }
+  static __device__ __forceinline__ void store_a(const Params&, const AFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+    const int row = t & 127, c0 = (t >> 7) * 4;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        v[j] = (co < p.Cout && k + j < p.red) ? __ldg(p.wt + (long long)co * p.red + k + j) : 0.0f;
-      store_chunk<SPLIT3>(hi, lo, row, c, make_float4(v[0], v[1], v[2], v[3]));
-    }
+    for (int c = 0; c < 4; ++c)
+      store_chunk<SPLIT3>(hi, lo, row, c0 + c,
+                          make_float4(f.v[c * 4], f.v[c * 4 + 1], f.v[c * 4 + 2], f.v[c * 4 + 3]));
+  }
+  static __device__ __forceinline__ void load_b(const Params& p, const uint8_t*, int n0, int kb, int t, BFrag& f) {
+    load_weights<BN, 32 * NB>(f, t, [&](int row, int kk) {
+      const int co = n0 + row, k = kb * KB + kk;
+      return (co < p.Cout && k < p.red) ? __ldg(p.wt + (long long)co * p.red + k) : 0.0f;
+    });
+  }
+  static __device__ __forceinline__ void store_b(const Params&, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+    store_weights<BN, SPLIT3, 32 * NB>(f, hi, lo, t);
   }
   template <int HALF>
   static __device__ __forceinline__ void epilogue(const Params& p, int mrow, int nb, const float* acc, int) {
@@ -142,61 +183,70 @@ struct ConvFwdProblem {
 };
 
 // ------------------------------------------------------------ backward data --------
+struct DgradRow {
+  const float* ptr;   // dY + n*Cout*OH*OW
+  int ty0, tx0;
+  bool ok;
+};
+
 template <int BN, bool SPLIT3>
 struct ConvDgradProblem {
   using Params = ConvParams;
-  static __device__ __forceinline__ void init(const Params& p, uint8_t* scratch, int tid) {
+  static constexpr int NA = 8, NB = 4, KC = 8;
+  using AState = DgradRow;
+  static __device__ __forceinline__ void init(const Params& p, uint8_t* scratch, int tid, int nt) {
     uint32_t* tab = reinterpret_cast<uint32_t*>(scratch);
     const int KK = p.K * p.K;
-    for (int k = tid; k < p.nkb * KB; k += THREADS) {
+    for (int k = tid; k < p.nkb * KB; k += nt) {
       const int co = k / KK, r = k - co * KK, ky = r / p.K, kx = r - ky * p.K;
       tab[k] = pack_tap(co * p.OH * p.OW, ky, kx, k < p.red, 0);
     }
   }
-  static __device__ __forceinline__ void produce_a(const Params& p, const uint8_t* scratch, int m0,
-                                                   int kb, uint8_t* hi, uint8_t* lo, int t) {
-    const uint32_t* tab = reinterpret_cast<const uint32_t*>(scratch) + kb * KB;
-    const long long m = (long long)m0 + t;
-    const bool rowok = m < p.rows;
+  static __device__ __forceinline__ void a_setup(const Params& p, const uint8_t*, int m0, int t, AState& st) {
+    const long long m = (long long)m0 + (t & 127);
+    st.ok = m < p.rows;
     const int hw = p.H * p.W;
-    const int n = rowok ? (int)(m / hw) : 0;
-    const int pix = rowok ? (int)(m - (long long)n * hw) : 0;
+    const int n = st.ok ? (int)(m / hw) : 0;
+    const int pix = st.ok ? (int)(m - (long long)n * hw) : 0;
     const int iy = pix / p.W, ix = pix - iy * p.W;
-    const int ty0 = iy + p.P, tx0 = ix + p.P;
-    const long long base = (long long)n * p.Cout * p.OH * p.OW;
+    st.ty0 = iy + p.P; st.tx0 = ix + p.P;
+    st.ptr = p.src + (long long)n * p.Cout * p.OH * p.OW;
+  }
+  using AFrag = Frag<16>;
+  using BFrag = Frag<BN / 4>;
+  static __device__ __forceinline__ void load_a(const Params& p, const AState& st, const uint8_t* scratch,
+                                                int, int kb, int t, AFrag& f) {
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(scratch) + kb * KB + (t >> 7) * 16;
     const int smask = p.S - 1;
-#pragma unroll 2
-    for (int c = 0; c < 8; ++c) {
-      float v[4];
+    float* v = f.v;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t e = tab[c * 4 + j];
-        const int ty = ty0 - (int)((e >> 20) & 15), tx = tx0 - (int)((e >> 24) & 15);
-        const int oy = ty >> p.logS, ox = tx >> p.logS;
-        const bool ok = rowok && ((e >> 28) & 1) && ty >= 0 && tx >= 0 && !((ty | tx) & smask) &&
-                        oy < p.OH && ox < p.OW;
-        v[j] = ok ? __ldg(p.src + base + (e & 0xFFFFF) + oy * p.OW + ox) : 0.0f;
-      }
-      store_chunk<SPLIT3>(hi, lo, t, c, make_float4(v[0], v[1], v[2], v[3]));
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t e = tab[j];
+      const int ty = st.ty0 - (int)((e >> 20) & 15), tx = st.tx0 - (int)((e >> 24) & 15);
+      const int oy = ty >> p.logS, ox = tx >> p.logS;
+      const bool ok = st.ok && ((e >> 28) & 1) && ty >= 0 && tx >= 0 && !((ty | tx) & smask) &&
+                      oy < p.OH && ox < p.OW;
+      v[j] = ok ? __ldg(st.ptr + (int)(e & 0xFFFFF) + oy * p.OW + ox) : 0.0f;
     }
   }
-  static __device__ __forceinline__ void produce_b(const Params& p, const uint8_t*, int n0, int kb,
-                                                   uint8_t* hi, uint8_t* lo, int t) {
+  static __device__ __forceinline__ void store_a(const Params&, const AFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+    const int row = t & 127, c0 = (t >> 7) * 4;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      store_chunk<SPLIT3>(hi, lo, row, c0 + c,
+                          make_float4(f.v[c * 4], f.v[c * 4 + 1], f.v[c * 4 + 2], f.v[c * 4 + 3]));
+  }
+  static __device__ __forceinline__ void load_b(const Params& p, const uint8_t*, int n0, int kb, int t, BFrag& f) {
     // B[ci][k = (co,ky,kx)] = wt[((co*Cin + ci)*K + ky)*K + kx]
     const int KK = p.K * p.K;
-#pragma unroll
-    for (int i = 0; i < BN * 8 / PROD_THREADS; ++i) {
-      const int u = i * PROD_THREADS + t, row = u % BN, c = u / BN;
-      const int ci = n0 + row;
-      float v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = kb * KB + c * 4 + j;
-        const int co = k / KK, r = k - co * KK;
-        v[j] = (ci < p.Cin && k < p.red) ? __ldg(p.wt + ((long long)co * p.Cin + ci) * KK + r) : 0.0f;
-      }
-      store_chunk<SPLIT3>(hi, lo, row, c, make_float4(v[0], v[1], v[2], v[3]));
-    }
+    load_weights<BN, 32 * NB>(f, t, [&](int row, int kk) {
+      const int ci = n0 + row, k = kb * KB + kk;
+      const int co = k / KK, r = k - co * KK;
+      return (ci < p.Cin && k < p.red) ? __ldg(p.wt + ((long long)co * p.Cin + ci) * KK + r) : 0.0f;
+    });
+  }
+  static __device__ __forceinline__ void store_b(const Params&, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+    store_weights<BN, SPLIT3, 32 * NB>(f, hi, lo, t);
   }
   template <int HALF>
   static __device__ __forceinline__ void epilogue(const Params& p, int mrow, int nb, const float* acc, int) {
@@ -218,58 +268,44 @@ struct ConvDgradProblem {
 template <int BN, bool SPLIT3>
 struct ConvWgradProblem {
   using Params = ConvParams;
-  static __device__ __forceinline__ void init(const Params& p, uint8_t* scratch, int tid) {
-    // table over the D rows (taps) of this CTA's m tiles is rebuilt per tile from the
-    // global tap index; here: one entry per tap of the whole layer (<= 1024)
-    uint32_t* tab = reinterpret_cast<uint32_t*>(scratch);
+  // short TMEM chains: the reduction runs over millions of cancelling terms, and the
+  // accumulator's truncation is a bias, not noise (see tc_core.cuh)
+  static constexpr int NA = 8, NB = 4, KC = 2;
+  struct AState {};
+  static __device__ __forceinline__ void init(const Params& p, uint8_t* scratch, int tid, int nt) {
+    uint32_t* tab = reinterpret_cast<uint32_t*>(scratch);   // one entry per tap row of the layer
     const int KK = p.K * p.K;
     const int plane = p.use_view ? (int)p.view.stride_c : p.H * p.W;
-    for (int m = tid; m < p.mrows; m += THREADS) {
+    for (int m = tid; m < p.mrows; m += nt) {
       const int ci = m / KK, r = m - ci * KK, ky = r / p.K, kx = r - ky * p.K;
       tab[m] = pack_tap(ci * plane + ky * p.W + kx, ky, kx, m < (int)p.rows, ci);
     }
   }
-  // lane <-> pixel of the k-block; the warp walks over its 32 rows (taps)
-  static __device__ __forceinline__ void produce_a(const Params& p, const uint8_t* scratch, int m0,
-                                                   int kb, uint8_t* hi, uint8_t* lo, int t) {
-    const uint32_t* tab = reinterpret_cast<const uint32_t*>(scratch) + m0;
+  static __device__ __forceinline__ void a_setup(const Params&, const uint8_t*, int, int, AState&) {}
+  // lane <-> pixel of the k-block; warp w walks over its 16 tap rows
+  using AFrag = Frag<16>;
+  using BFrag = Frag<BN / 4>;
+  static __device__ __forceinline__ void load_a(const Params& p, const AState&, const uint8_t* scratch,
+                                                int m0, int kb, int t, AFrag& f) {
     const int lane = t & 31, w = t >> 5;
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(scratch) + m0 + w * 16;
     const long long px = (long long)kb * KB + lane;
     const bool pok = px < p.red;
     const int ohw = p.OH * p.OW;
     const int n = pok ? (int)(px / ohw) : 0;
     const int pix = pok ? (int)(px - (long long)n * ohw) : 0;
     const int oy = pix / p.OW, ox = pix - oy * p.OW;
-    const int iy0 = oy * p.S - p.P, ix0 = ox * p.S - p.P;
-    long long base;
-    uint32_t cmask = 0xffffffffu;
-    if (p.use_view) {
-      const long long r = n / p.view.T;
-      const int tt = n - (int)r * p.view.T;
-      base = r * p.view.stride_r + (long long)tt * p.view.stride_t + (long long)iy0 * p.W + ix0;
-      cmask = view_chanmask(p.view, r, tt);
-    } else {
-      base = (long long)n * p.Cin * p.H * p.W + (long long)iy0 * p.W + ix0;
-    }
-#pragma unroll 4
-    for (int rr = 0; rr < 32; ++rr) {
-      const int row = w * 32 + rr;
-      const uint32_t e = tab[row];
-      const int ky = (e >> 20) & 15, kx = (e >> 24) & 15;
-      const bool ok = pok && ((e >> 28) & 1) && (unsigned)(iy0 + ky) < (unsigned)p.H &&
-                      (unsigned)(ix0 + kx) < (unsigned)p.W && ((cmask >> (e >> 29)) & 1);
-      float x = 0.0f;
-      if (ok) {
-        const long long a = base + (e & 0xFFFFF);
-        if (p.use_view && p.view.dtype == 0) x = (float)static_cast<const uint8_t*>(p.view.base)[a];
-        else if (p.use_view) x = static_cast<const float*>(p.view.base)[a];
-        else x = __ldg(p.src + a);
-      }
-      store_elem<SPLIT3>(hi, lo, row, lane, x);
-    }
+    XRow xr;
+    xrow_setup(p, pok, n, oy * p.S - p.P, ox * p.S - p.P, xr);
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) f.v[rr] = xrow_load(p, xr, tab[rr]);
   }
-  static __device__ __forceinline__ void produce_b(const Params& p, const uint8_t*, int n0, int kb,
-                                                   uint8_t* hi, uint8_t* lo, int t) {
+  static __device__ __forceinline__ void store_a(const Params&, const AFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+    const int lane = t & 31, w = t >> 5;
+#pragma unroll
+    for (int rr = 0; rr < 16; ++rr) store_elem<SPLIT3>(hi, lo, w * 16 + rr, lane, f.v[rr]);
+  }
+  static __device__ __forceinline__ void load_b(const Params& p, const uint8_t*, int n0, int kb, int t, BFrag& f) {
     const int lane = t & 31, w = t >> 5;
     const long long px = (long long)kb * KB + lane;
     const bool pok = px < p.red;
@@ -277,12 +313,18 @@ struct ConvWgradProblem {
     const int n = pok ? (int)(px / ohw) : 0;
     const int pix = pok ? (int)(px - (long long)n * ohw) : 0;
     const float* src = p.dy + (long long)n * p.Cout * ohw + pix;
-#pragma unroll 4
-    for (int rr = 0; rr < BN / 4; ++rr) {
-      const int row = w * (BN / 4) + rr, co = n0 + row;
-      const float x = (pok && co < p.Cout) ? __ldg(src + (long long)co * ohw) : 0.0f;
-      store_elem<SPLIT3>(hi, lo, row, lane, x);
+    constexpr int RW = BN / NB;
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+      const int co = n0 + w * RW + rr;
+      f.v[rr] = (pok && co < p.Cout) ? __ldg(src + (long long)co * ohw) : 0.0f;
     }
+  }
+  static __device__ __forceinline__ void store_b(const Params&, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+    const int lane = t & 31, w = t >> 5;
+    constexpr int RW = BN / NB;
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) store_elem<SPLIT3>(hi, lo, w * RW + rr, lane, f.v[rr]);
   }
   template <int HALF>
   static __device__ __forceinline__ void epilogue(const Params& p, int mrow, int nb, const float* acc,
@@ -340,9 +382,8 @@ static bool conv_tc_ok(const a2c_conv_shape* s) {
 
 template <template <int, bool> class Prob>
 static int launch_conv(const ConvParams& p, int ncols_needed, int mtiles, int splits, bool split3,
-                       cudaStream_t st, int* bn_out = nullptr) {
+                       cudaStream_t st) {
   const int bn = ncols_needed > 32 ? 64 : 32;
-  if (bn_out) *bn_out = bn;
   const int ntiles = cdiv(ncols_needed, bn);
   int rc;
   if (split3) {
@@ -383,7 +424,7 @@ int conv_fwd_tc_try(const float* X, const a2c_state_view* xview, const float* Wt
   p.rows = (long long)N * s->OH * s->OW;
   p.nkb = cdiv(red, tc::KB); p.kb_per_split = p.nkb;
   const long long mt = cdivll(p.rows, tc::TM);
-  if (mt > 0x7fffffff) return 1;
+  if (mt > 0x7fffffff / tc::TM) return 1;
   return tc::launch_conv<tc::ConvFwdProblem>(p, s->Cout, (int)mt, 1, precision == 1, st);
 }
 
@@ -399,17 +440,22 @@ int conv_dgrad_tc_try(const float* dY, const float* Wt, float* dX, int N, const 
   p.rows = (long long)N * s->H * s->W;
   p.nkb = cdiv(red, tc::KB); p.kb_per_split = p.nkb;
   const long long mt = cdivll(p.rows, tc::TM);
-  if (mt > 0x7fffffff) return 1;
+  if (mt > 0x7fffffff / tc::TM) return 1;
   return tc::launch_conv<tc::ConvDgradProblem>(p, s->Cin, (int)mt, 1, precision == 1, st);
 }
 
-long long conv_wgrad_tc_workspace(const a2c_conv_shape* s) {
+static void wgrad_plan(const a2c_conv_shape* s, int* mtiles, int* bn, int* ntiles, int* splits) {
   const int taps = s->Cin * s->K * s->K;
-  const int mtiles = cdiv(taps, tc::TM);
-  const int bn = s->Cout > 32 ? 64 : 32;
-  const int ntiles = cdiv(s->Cout, bn);
-  int splits = num_sms() / (mtiles * ntiles);
-  if (splits < 1) splits = 1;
+  *mtiles = cdiv(taps, tc::TM);
+  *bn = s->Cout > 32 ? 64 : 32;
+  *ntiles = cdiv(s->Cout, *bn);
+  int sp = num_sms() / (*mtiles * *ntiles);
+  *splits = sp < 1 ? 1 : sp;
+}
+
+long long conv_wgrad_tc_workspace(const a2c_conv_shape* s) {
+  int mtiles, bn, ntiles, splits;
+  wgrad_plan(s, &mtiles, &bn, &ntiles, &splits);
   return (long long)splits * mtiles * tc::TM * ntiles * bn * 4 + (long long)s->Cout * 8;
 }
 
@@ -418,10 +464,11 @@ int conv_wgrad_tc_try(const float* X, const a2c_state_view* xview, const float* 
                       long long workspace_bytes, int precision, cudaStream_t st) {
   if (!tc::conv_tc_ok(s)) return 1;
   const int taps = s->Cin * s->K * s->K;
-  const int mtiles = cdiv(taps, tc::TM);
+  int mtiles, bn, ntiles, splits;
+  wgrad_plan(s, &mtiles, &bn, &ntiles, &splits);
   if (mtiles * tc::TM * 4 > tc::SCRATCH_BYTES) return 1;
   const long long npix = (long long)N * s->OH * s->OW;
-  if (npix >= (1ll << 31)) return 1;
+  if (npix >= (1ll << 31) - 64) return 1;
   if (workspace_bytes < conv_wgrad_tc_workspace(s)) return 1;
   tc::ConvParams p;
   tc::fill_common(&p, s, N);
@@ -433,29 +480,21 @@ int conv_wgrad_tc_try(const float* X, const a2c_state_view* xview, const float* 
   p.red = (int)npix;
   p.rows = taps;
   p.nkb = (int)cdivll(npix, tc::KB);
-  const int bn = s->Cout > 32 ? 64 : 32;
-  const int ntiles = cdiv(s->Cout, bn);
-  int splits = num_sms() / (mtiles * ntiles);
-  if (splits < 1) splits = 1;
-  int kps = cdiv(cdiv(p.nkb, splits), tc::KC) * tc::KC;     // whole accumulation chunks per split
+  int kps = cdiv(cdiv(p.nkb, splits), 8) * 8;     // whole accumulation chunks per split
   splits = cdiv(p.nkb, kps);
   p.kb_per_split = kps;
   p.mrows = mtiles * tc::TM;
   p.ncols = ntiles * bn;
   double* bias_acc = reinterpret_cast<double*>(workspace);
   p.out = reinterpret_cast<float*>(bias_acc + s->Cout);
-  // the grid's y dimension walks the m tiles: every (m tile, n tile, split) is one CTA here
   int rc;
-  {
-    // mtiles CTAs in y (no persistence needed: few tiles), splits in z
-    const bool split3 = precision == 1;
-    if (split3) {
-      rc = bn == 64 ? tc::tc_launch<64, true, tc::ConvWgradProblem<64, true>>(p, mtiles, ntiles, splits, st)
-                    : tc::tc_launch<32, true, tc::ConvWgradProblem<32, true>>(p, mtiles, ntiles, splits, st);
-    } else {
-      rc = bn == 64 ? tc::tc_launch<64, false, tc::ConvWgradProblem<64, false>>(p, mtiles, ntiles, splits, st)
-                    : tc::tc_launch<32, false, tc::ConvWgradProblem<32, false>>(p, mtiles, ntiles, splits, st);
-    }
+  const bool split3 = precision == 1;
+  if (split3) {
+    rc = bn == 64 ? tc::tc_launch<64, true, tc::ConvWgradProblem<64, true>>(p, mtiles, ntiles, splits, st)
+                  : tc::tc_launch<32, true, tc::ConvWgradProblem<32, true>>(p, mtiles, ntiles, splits, st);
+  } else {
+    rc = bn == 64 ? tc::tc_launch<64, false, tc::ConvWgradProblem<64, false>>(p, mtiles, ntiles, splits, st)
+                  : tc::tc_launch<32, false, tc::ConvWgradProblem<32, false>>(p, mtiles, ntiles, splits, st);
   }
   if (rc) return rc;
   g_launches++;

@@ -2,10 +2,10 @@
 //
 // One CTA computes a 128 x BN fp32 tile  D = sum_k A[m,k] * B[n,k]  on the 5th-gen
 // tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM):
-//   warps 0-3   producers of the A tile   (Problem::produce_a)
-//   warps 4-7   producers of the B tile   (Problem::produce_b)
-//   warps 8-15  accumulator drain + epilogue (Problem::epilogue)
-//   warp  16    MMA issuer (one elected lane), warp 17 TMEM allocator
+//   NA warps    producers of the A tile   (Problem::produce_a)
+//   NB warps    producers of the B tile   (Problem::produce_b)
+//   8 warps     accumulator drain + epilogue (Problem::epilogue)
+//   1 warp      MMA issuer (one elected lane);  1 warp TMEM allocator
 // Operand tiles live in shared memory in the canonical K-major SWIZZLE_128B UMMA
 // layout: rows of 32 fp32 (128 B), 16-byte chunk index XOR (row & 7), 8-row
 // groups 1024 B apart.  Producers are ordinary threads, so a Problem can gather
@@ -26,12 +26,9 @@ namespace tc {
 
 constexpr int TM = 128;            // UMMA M (cta_group::1)
 constexpr int KB = 32;             // k-block: 32 fp32 = one 128-byte swizzle row
-constexpr int PROD_THREADS = 128;  // per operand
-constexpr int THREADS = 576;       // 18 warps
-constexpr int NUM_PROD_WARPS = 8;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int KC = 8;              // k-blocks per TMEM accumulation chunk (256 k)
 constexpr int SCRATCH_BYTES = 4096;  // per-CTA scratch handed to Problem::init
+constexpr int MAX_THREADS = 704;     // 8 A + 4 B producer warps + 8 drain + MMA + allocator
 
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -111,13 +108,24 @@ __device__ __forceinline__ void store_elem(uint8_t* hi_tile, uint8_t* lo_tile, i
 }
 
 // Problem concept:
+//   static constexpr int NA, NB;      producer warps for A / B (NA + NB a multiple of 4)
+//   static constexpr int KC;          k-blocks chained in one TMEM accumulator before it is drained
 //   struct Params { ...; int nkb; int kb_per_split; };        (nkb = total k-blocks)
-//   static __device__ void init(const Params&, uint8_t* scratch, int tid);      all threads, before the main loop
-//   static __device__ void produce_a(const Params&, const uint8_t* scratch, int m0, int kb, uint8_t* hi, uint8_t* lo, int t);
-//   static __device__ void produce_b(const Params&, const uint8_t* scratch, int n0, int kb, uint8_t* hi, uint8_t* lo, int t);
-//   static __device__ void epilogue(const Params&, int m, int n_begin, const float* acc, int count, int split);
+//   struct AState;                    per-thread, per-m-tile producer state (row decode etc.)
+//   static __device__ void init(const Params&, uint8_t* scratch, int tid, int nthreads);
+//   static __device__ void a_setup(const Params&, const uint8_t* scratch, int m0, int t, AState&);
+//   static __device__ void produce_a(const Params&, const AState&, const uint8_t* scratch, int m0, int kb, hi, lo, int t);
+//   static __device__ void produce_b(const Params&, const uint8_t* scratch, int n0, int kb, hi, lo, int t);
+//   static __device__ void epilogue<HALF>(const Params&, int m, int n_begin, const float* acc, int split);
+// t = thread index within the operand's producer warps.
 template <int BN, bool SPLIT3, class P>
-__global__ void __launch_bounds__(THREADS, 1) tc_kernel(const typename P::Params p, int stages, int mtiles) {
+__global__ void __launch_bounds__(32 * (P::NA + P::NB + NUM_EPI_WARPS + 2), 1)
+tc_kernel(const typename P::Params p, int stages, int mtiles) {
+  constexpr int NUM_PROD_WARPS = P::NA + P::NB;
+  constexpr int KC = P::KC;
+  constexpr int EPI0 = NUM_PROD_WARPS, MMA_WARP = EPI0 + NUM_EPI_WARPS, ALLOC_WARP = MMA_WARP + 1;
+  constexpr int THREADS = 32 * (ALLOC_WARP + 1);
+  static_assert(NUM_PROD_WARPS % 4 == 0, "drain warps must start at a multiple of 4 (TMEM lane quarters)");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_BYTES = TM * 128, B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (A_BYTES + B_BYTES);
@@ -150,13 +158,13 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const typename P::Params
     }
     mbar_fence_init();
   }
-  if (warp == 17) {
+  if (warp == ALLOC_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
                  "r"((uint32_t)(2 * BN)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  P::init(p, scratch, threadIdx.x);
+  P::init(p, scratch, threadIdx.x, THREADS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -164,29 +172,59 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const typename P::Params
 
   auto stage_ptr = [&](int s) { return smem + s * STAGE_BYTES; };
   // stage layout: [A_hi][A_lo?][B_hi][B_lo?]
-  if (warp < NUM_PROD_WARPS) {
-    const bool isA = warp < 4;
-    const int t = threadIdx.x & (PROD_THREADS - 1);
-    int it = 0;
-    for (int mt = blockIdx.y; mt < mtiles; mt += gridDim.y) {
-      const int m0 = mt * TM;
-      for (int i = 0; i < nkb; ++i, ++it) {
-        const int s = it % stages;
-        const uint32_t parity = (it / stages) & 1;
-        mbar_wait(&empty[s], parity ^ 1);
-        uint8_t* st = stage_ptr(s);
-        if (isA) {
-          P::produce_a(p, scratch, m0, kb_begin + i, st, st + A_BYTES, t);
-        } else {
-          uint8_t* b = st + (SPLIT3 ? 2 : 1) * A_BYTES;
-          P::produce_b(p, scratch, n0, kb_begin + i, b, b + B_BYTES, t);
+  if (warp < P::NA) {
+    // ---- A producers: the global loads of k-block i+1 are issued before k-block i is
+    // converted and stored, so their latency overlaps the stage hand-shake and the stores
+    const int t = threadIdx.x;
+    int mt = blockIdx.y, i = 0, it = 0;
+    if (mt < mtiles && nkb > 0) {
+      typename P::AState ast;
+      typename P::AFrag cur, nxt;
+      P::a_setup(p, scratch, mt * TM, t, ast);
+      P::load_a(p, ast, scratch, mt * TM, kb_begin, t, cur);
+      while (true) {
+        int ni = i + 1, nmt = mt;
+        if (ni == nkb) { ni = 0; nmt = mt + gridDim.y; }
+        const bool has_next = nmt < mtiles;
+        if (has_next) {
+          if (nmt != mt) P::a_setup(p, scratch, nmt * TM, t, ast);
+          P::load_a(p, ast, scratch, nmt * TM, kb_begin + ni, t, nxt);
         }
+        const int s = it % stages;
+        mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        uint8_t* st = stage_ptr(s);
+        P::store_a(p, cur, st, st + A_BYTES, t);
         fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
+        if (!has_next) break;
+        cur = nxt; mt = nmt; i = ni; ++it;
       }
     }
-  } else if (warp == 16) {
+  } else if (warp < NUM_PROD_WARPS) {
+    // ---- B producers (same pipelining; the B tile depends on the k-block only)
+    const int t = (int)threadIdx.x - 32 * P::NA;
+    int mt = blockIdx.y, i = 0, it = 0;
+    if (mt < mtiles && nkb > 0) {
+      typename P::BFrag cur, nxt;
+      P::load_b(p, scratch, n0, kb_begin, t, cur);
+      while (true) {
+        int ni = i + 1, nmt = mt;
+        if (ni == nkb) { ni = 0; nmt = mt + gridDim.y; }
+        const bool has_next = nmt < mtiles;
+        if (has_next) P::load_b(p, scratch, n0, kb_begin + ni, t, nxt);
+        const int s = it % stages;
+        mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        uint8_t* b = stage_ptr(s) + (SPLIT3 ? 2 : 1) * A_BYTES;
+        P::store_b(p, cur, b, b + B_BYTES, t);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[s]);
+        if (!has_next) break;
+        cur = nxt; mt = nmt; i = ni; ++it;
+      }
+    }
+  } else if (warp == MMA_WARP) {
     constexpr uint32_t idesc = make_idesc(BN);
     int it = 0, gchunk0 = 0;
     for (int mt = blockIdx.y; mt < mtiles; mt += gridDim.y, gchunk0 += nchunks)
@@ -223,9 +261,9 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const typename P::Params
       }
       __syncwarp();
     }
-  } else if (warp >= 8 && warp < 8 + NUM_EPI_WARPS) {
+  } else if (warp >= EPI0 && warp < EPI0 + NUM_EPI_WARPS) {
     // ---- drain + epilogue: thread <-> accumulator row (TMEM lane), half of the columns ----
-    const int e = warp - 8, q = e & 3, hsel = e >> 2;
+    const int e = warp - EPI0, q = e & 3, hsel = e >> 2;
     int gchunk = 0;
     for (int mt = blockIdx.y; mt < mtiles; mt += gridDim.y) {
     const int m0 = mt * TM;
@@ -260,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1) tc_kernel(const typename P::Params
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) {
+  if (warp == ALLOC_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)(2 * BN)));
@@ -293,7 +331,7 @@ int tc_launch(const typename P::Params& p, int mtiles, int ntiles, int splits, c
   const int cap = num_sms() / (ntiles * splits > 0 ? ntiles * splits : 1);
   if (gy > cap) gy = cap < 1 ? 1 : cap;
   dim3 grid(ntiles, gy, splits);
-  kern<<<grid, THREADS, smem, st>>>(p, stages, mtiles);
+  kern<<<grid, 32 * (P::NA + P::NB + NUM_EPI_WARPS + 2), smem, st>>>(p, stages, mtiles);
   return 0;
 }
 
