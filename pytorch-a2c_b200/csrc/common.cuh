@@ -111,5 +111,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// For waits that are expected to be long (a role that is ahead of the pipeline): back off
+// so the spinning warp does not take issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
+
+// Stage index + phase parity of a circular mbarrier pipeline, advanced without div/mod.
+struct StageRing {
+  int s, n;
+  uint32_t par;
+  __device__ __forceinline__ explicit StageRing(int n_) : s(0), n(n_), par(0) {}
+  __device__ __forceinline__ void next() {
+    if (++s == n) { s = 0; par ^= 1u; }
+  }
+};
 
 }  // namespace a2c

@@ -466,6 +466,15 @@ int conv_wgrad_tc_try(const float* X, const a2c_state_view* xview, const float* 
                       float* dbias, int N, const a2c_conv_shape* s, void* workspace,
                       long long workspace_bytes, int precision, cudaStream_t st);
 
+int conv_fwd_patch_try(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias,
+                       float* Y, int N, const a2c_conv_shape* s, int relu, int precision, cudaStream_t st);
+int conv_dgrad_patch_try(const float* dY, const float* Wt, float* dX, int N, const a2c_conv_shape* s,
+                         int precision, cudaStream_t st);
+long long conv_wgrad_patch_workspace(const a2c_conv_shape* s);
+int conv_wgrad_patch_try(const float* X, const a2c_state_view* xview, const float* dY, float* dW,
+                         float* dbias, int N, const a2c_conv_shape* s, void* workspace,
+                         long long workspace_bytes, int precision, cudaStream_t st);
+
 }  // namespace a2c
 
 using namespace a2c;
@@ -479,7 +488,9 @@ int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
   if (N == 0) return 0;
   if (precision != 0) {
     A2C_ARG_CHECK(xview || X, "conv_fwd: null input");
-    int rc = conv_fwd_tc_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
+    int rc = conv_fwd_patch_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
+    if (rc != 1) return rc;
+    rc = conv_fwd_tc_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
     if (rc != 1) return rc;
   }
   ConvFwdParams p{};
@@ -495,7 +506,9 @@ int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, fl
   A2C_ARG_CHECK(dY && Wt && dX && N >= 0, "conv_bwd_data: bad args");
   if (N == 0) return 0;
   if (precision != 0 && !Ymask) {
-    int rc = conv_dgrad_tc_try(dY, Wt, dX, N, s, precision, as_stream(stream));
+    int rc = conv_dgrad_patch_try(dY, Wt, dX, N, s, precision, as_stream(stream));
+    if (rc != 1) return rc;
+    rc = conv_dgrad_tc_try(dY, Wt, dX, N, s, precision, as_stream(stream));
     if (rc != 1) return rc;
   }
   // dX = stride-1 conv of the dilated, masked dY with flipped/transposed weights
@@ -517,7 +530,9 @@ long long a2c_conv2d_bwd_weight_workspace(const a2c_conv_shape* s) {
   if (plan_wgrad(s, &pl)) return 0;
   const long long simt = (long long)pl.grid * pl.PG *
                          ((long long)s->Cout * s->Cin * s->K * s->K + s->Cout) * (long long)sizeof(float);
-  const long long tcw = conv_wgrad_tc_workspace(s);
+  long long tcw = conv_wgrad_tc_workspace(s);
+  const long long pw = conv_wgrad_patch_workspace(s);
+  if (pw > tcw) tcw = pw;
   return simt > tcw ? simt : tcw;
 }
 
@@ -538,7 +553,9 @@ int a2c_conv2d_bwd_weight(const float* X, const a2c_state_view* xview, const flo
   }
   if (precision != 0 && !Ymask) {
     A2C_ARG_CHECK(xview || X, "conv_bwd_weight: null input");
-    int rc = conv_wgrad_tc_try(X, xview, dY, dW, dbias, N, s, workspace, workspace_bytes, precision, st);
+    int rc = conv_wgrad_patch_try(X, xview, dY, dW, dbias, N, s, workspace, workspace_bytes, precision, st);
+    if (rc != 1) return rc;
+    rc = conv_wgrad_tc_try(X, xview, dY, dW, dbias, N, s, workspace, workspace_bytes, precision, st);
     if (rc != 1) return rc;
   }
   WgPlan pl;

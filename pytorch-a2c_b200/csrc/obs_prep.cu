@@ -187,6 +187,7 @@ materialize_kernel(a2c_state_view v, OutT* __restrict__ out, long long N) {
   }
 }
 
+void* tensormap_encoder();   // shared with the conv patch kernels
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
@@ -198,6 +199,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   }
   return fn;
 }
+
+void* tensormap_encoder() { return reinterpret_cast<void*>(get_encode()); }
 
 static int launch_prep(const uint8_t* frames, const uint8_t* reset, uint8_t* planes, uint8_t* pflag,
                        int R, int F, int P, int j0, int variant, cudaStream_t st) {

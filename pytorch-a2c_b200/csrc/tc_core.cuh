@@ -131,7 +131,8 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
   constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (A_BYTES + B_BYTES);
   constexpr int HALF = BN / 2;      // columns per drain warp
   // 1024-byte alignment of every tile is required by SWIZZLE_128B
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the shared array keeps the shared address space: LDS/STS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* scratch = smem + stages * STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(scratch + SCRATCH_BYTES);
   uint64_t* empty = full + stages;
@@ -177,6 +178,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
     // converted and stored, so their latency overlaps the stage hand-shake and the stores
     const int t = threadIdx.x;
     int mt = blockIdx.y, i = 0, it = 0;
+    StageRing ring(stages);
     if (mt < mtiles && nkb > 0) {
       typename P::AState ast;
       typename P::AFrag cur, nxt;
@@ -190,21 +192,22 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
           if (nmt != mt) P::a_setup(p, scratch, nmt * TM, t, ast);
           P::load_a(p, ast, scratch, nmt * TM, kb_begin + ni, t, nxt);
         }
-        const int s = it % stages;
-        mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        const int s = ring.s;
+        mbar_wait(&empty[s], ring.par ^ 1);
         uint8_t* st = stage_ptr(s);
         P::store_a(p, cur, st, st + A_BYTES, t);
         fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
         if (!has_next) break;
-        cur = nxt; mt = nmt; i = ni; ++it;
+        cur = nxt; mt = nmt; i = ni; ++it; ring.next();
       }
     }
   } else if (warp < NUM_PROD_WARPS) {
     // ---- B producers (same pipelining; the B tile depends on the k-block only)
     const int t = (int)threadIdx.x - 32 * P::NA;
     int mt = blockIdx.y, i = 0, it = 0;
+    StageRing ring(stages);
     if (mt < mtiles && nkb > 0) {
       typename P::BFrag cur, nxt;
       P::load_b(p, scratch, n0, kb_begin, t, cur);
@@ -213,24 +216,25 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
         if (ni == nkb) { ni = 0; nmt = mt + gridDim.y; }
         const bool has_next = nmt < mtiles;
         if (has_next) P::load_b(p, scratch, n0, kb_begin + ni, t, nxt);
-        const int s = it % stages;
-        mbar_wait(&empty[s], ((it / stages) & 1) ^ 1);
+        const int s = ring.s;
+        mbar_wait(&empty[s], ring.par ^ 1);
         uint8_t* b = stage_ptr(s) + (SPLIT3 ? 2 : 1) * A_BYTES;
         P::store_b(p, cur, b, b + B_BYTES, t);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
         if (!has_next) break;
-        cur = nxt; mt = nmt; i = ni; ++it;
+        cur = nxt; mt = nmt; i = ni; ++it; ring.next();
       }
     }
   } else if (warp == MMA_WARP) {
     constexpr uint32_t idesc = make_idesc(BN);
     int it = 0, gchunk0 = 0;
+    StageRing ring(stages);
     for (int mt = blockIdx.y; mt < mtiles; mt += gridDim.y, gchunk0 += nchunks)
-    for (int i = 0; i < nkb; ++i, ++it) {
-      const int s = it % stages;
-      const uint32_t parity = (it / stages) & 1;
+    for (int i = 0; i < nkb; ++i, ++it, ring.next()) {
+      const int s = ring.s;
+      const uint32_t parity = ring.par;
       const int chunk = gchunk0 + i / KC, buf = chunk & 1;
       if (i % KC == 0) {                        // new chunk: its TMEM buffer must have been drained
         mbar_wait(&acc_empty[buf], ((chunk >> 1) & 1) ^ 1);
@@ -272,7 +276,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
     for (int j = 0; j < HALF; ++j) acc[j] = 0.0f;
     for (int chunk = 0; chunk < nchunks; ++chunk, ++gchunk) {
       const int buf = gchunk & 1;
-      mbar_wait(&acc_full[buf], (gchunk >> 1) & 1);
+      mbar_wait_relaxed(&acc_full[buf], (gchunk >> 1) & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + hsel * HALF;
 #pragma unroll
