@@ -64,6 +64,7 @@ struct PatchParams {
   int ncols;                             // wgrad partial pitch
   int stages, patch_bufs, patch_floats;  // patch_floats: SC*PH*PW rounded up to 32
   int use_tma;                           // patch staged by one TMA box per tile (f32 NCHW source)
+  int kc;                                // fwd / dgrad: k-blocks chained in TMEM before a drain
   int b_resident;                        // fwd / dgrad: all weight k-blocks live in smem for the whole kernel
   int stage_bytes;                       // bytes of one pipeline stage (A [+ B when streamed])
   // 16-bit tables keep the whole parameter block under the classic 4 KB limit (the TMA
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_patch_fwd_kernel(const __gr
   constexpr int A_BYTES = TM * 128, B_BYTES = BN * 128;
   constexpr int APAIR = (SPLIT3 ? 2 : 1) * A_BYTES, BPAIR = (SPLIT3 ? 2 : 1) * B_BYTES;
   constexpr int HALF = BN / 2;
-  constexpr int KC = 8;
+  const int KC = p.kc;   // forward: 1 (activations feed ReLU masks: keep the truncating TMEM chains short)
   PatchSmem sm = carve(smem_raw, p, p.b_resident ? p.nkb * BPAIR : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = p.N * p.tiles_y * p.tiles_x;
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_patch_wgrad_kernel(const __
   constexpr int A_BYTES = TM * 128, B_BYTES = BN * 128;
   constexpr int STAGE_BYTES = (SPLIT3 ? 2 : 1) * (A_BYTES + B_BYTES);
   constexpr int HALF = BN / 2;
-  constexpr int KC = 2;                       // short TMEM chains: truncation is a bias (tc_core.cuh)
+  constexpr int KC = 1;                       // shortest TMEM chains: truncation is a bias (tc_core.cuh)
   constexpr int KBT = (PT_TH * PT_TW) / KB;   // 4 k-blocks (of 32 positions) per spatial tile
   PatchSmem sm = carve(smem_raw, p, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -822,6 +823,7 @@ int conv_fwd_patch_try(const float* X, const a2c_state_view* xview, const float*
   for (int k = nk; k < p.nkb * tc::KB; ++k) p.delta[k] = tc::NOTAP16;
   p.wt = Wt; p.wstride_j = nk; p.J = s->Cout; p.bias = bias; p.relu = relu;
   p.out = Y; p.OutH = s->OH; p.OutW = s->OW; p.OS = 1; p.oa = 0; p.ob = 0;
+  p.kc = 1;
   return tc::dispatch_fwd_like(p, precision == 1, st);
 }
 
@@ -870,6 +872,7 @@ int conv_dgrad_patch_try(const float* dY, const float* Wt, float* dX, int N, con
       for (int kk = k; kk < p.nkb * tc::KB; ++kk) p.delta[kk] = tc::NOTAP16;
       p.wt = Wt; p.wstride_j = KK; p.J = s->Cin; p.bias = nullptr; p.relu = 0;
       p.out = dX; p.OutH = s->H; p.OutW = s->W; p.OS = S; p.oa = a; p.ob = b;
+      p.kc = 8;
       int rc = tc::dispatch_fwd_like(p, precision == 1, st);
       if (rc) return rc == 1 && (a | b) ? A2C_ERR_ARG : rc;
     }
