@@ -144,7 +144,7 @@ int a2c_loss_fwd_bwd(const float* logits, const float* vals, const long long* ac
  * column n; relu != 0 applies max(0, .); beta is 0 or 1.  `workspace` (may be
  * NULL) of `workspace_bytes` enables split-K for skinny outputs.
  * precision: 0 = fp32 FFMA; 1 = 3xTF32 on tcgen05 when the shape qualifies
- * (falls back to 0 otherwise); 2 = bf16 on tcgen05 (stated tolerance). */
+ * (falls back to 0 otherwise); 2 = single-pass TF32 on tcgen05 (tolerance 2e-3). */
 int a2c_gemm(const float* A, long long sam, long long sak, const float* B, long long sbk,
              long long sbn, float* C, long long ldc, const float* bias, int M, int N, int K,
              int relu, int beta, int precision, void* workspace, long long workspace_bytes,

@@ -320,7 +320,7 @@ class Conv2dFn(torch.autograd.Function):
         sig = "%d:%d>%d,%dx%d,k%ds%d" % (N, Cin, Cout, H, Wd, K, stride)
         call("a2c_conv2d_fwd", None if is_view else ptr(x), C.byref(x.c) if is_view else None,
              ptr(W), ptr(b), ptr(y), N, C.byref(s), 1 if relu else 0,
-             int(_os.environ.get("A2C_CONV_FWD_PRECISION", _PRECISION)), stream_ptr(),
+             _PRECISION, stream_ptr(),
              tag="a2c_conv2d_fwd|flops|" + sig, work=flops)
         ctx.flops, ctx.sig, ctx.precision = flops, sig, _PRECISION
         ctx.shape, ctx.relu, ctx.is_view, ctx.N = s, relu, is_view, N

@@ -7,10 +7,9 @@ initialised, and ``shared_data['states']`` may also be a
 uint8 tensor or an ``ops.View`` of the stage-1 plane ring.
 """
 import torch
-import torch.distributed as dist
 import torch.optim as optim
 
-from . import ops
+from . import ops, sharding
 from .utils import try_key
 
 
@@ -77,16 +76,19 @@ class Updater:
         self.ret_mean = None
         self.ret_std = None
         self._step = 0
+        self._count_cache = (None, None)
 
     # ---- distributed helpers (env-sharded ranks) ----------
-    @staticmethod
-    def _world():
-        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    _world = staticmethod(sharding.world_size)
+    _allreduce = staticmethod(sharding.allreduce_sum_)
 
-    def _allreduce(self, t):
-        if self._world() > 1:
-            dist.all_reduce(t)
-        return t
+    def _n_global(self, n_local):
+        """Transitions over all ranks; one tiny all-reduce, cached per local size."""
+        if self._world() == 1:
+            return n_local
+        if self._count_cache[0] != n_local:
+            self._count_cache = (n_local, sharding.global_count(n_local))
+        return self._count_cache[1]
 
     # ---- forward ------------------------------------------------------------
     def _to_dev(self, t):
@@ -119,7 +121,7 @@ class Updater:
         deltas = self._to_dev(shared_data['deltas']).reshape(-1).float()
         N = deltas.numel()
         world = self._world()
-        n_global = N * world
+        n_global = self._n_global(N)
 
         stats = torch.zeros(4, dtype=torch.float64, device=self.device)
         advs = ops.discount(deltas, dones, hyps['gamma'] * hyps['lambda_'], stats=stats[0:2])
@@ -135,9 +137,7 @@ class Updater:
             rets = returns if returns is not None else advs + vals.detach().reshape(-1)
             if world > 1:
                 s = torch.stack([rets.double().sum(), (rets.double() ** 2).sum()])
-                self._allreduce(s)
-                mean = s[0] / n_global
-                std = ((s[1] - n_global * mean * mean) / (n_global - 1)).clamp_min(0).sqrt()
+                mean, std = sharding.mean_unbiased_std(self._allreduce(s), n_global)
             else:
                 mean, std = rets.mean(), rets.std()
             if self.ret_mean is None:
@@ -153,9 +153,8 @@ class Updater:
                                                returns, stats[0:2], hyps, n_global=n_global,
                                                ret_norm=ret_norm)
         torch.autograd.backward([logits, vals], [dlogits, dvals.view_as(vals)])
-        if world > 1:
-            dist.all_reduce(self.flat.grad)
-            dist.all_reduce(out)
+        self._allreduce(self.flat.grad)
+        self._allreduce(out)
         return {"loss_terms": out, "advs": advs, "returns": returns, "vals": vals.detach(),
                 "logits": logits.detach(), "n_global": n_global}
 

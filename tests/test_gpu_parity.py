@@ -231,6 +231,33 @@ def test_loss_fwd_bwd(dev, N, A, norm, nstep):
     assert H.rel_err(dv.cpu().numpy(), vals.grad.numpy().reshape(-1)) < TOL
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("cut", [2560, 1000])
+def test_sharded_loss_contract(dev, cut):
+    """two env shards evaluated with the global advantage statistics and
+    n_global produce loss terms / gradients that add up to the full-batch ones
+    (the gloo side of the same contract: tests/test_distributed.py)."""
+    ops = ops_mod()
+    N, A = 5120, 3
+    gen = torch.Generator().manual_seed(5)
+    logits = (torch.randn(N, A, generator=gen) * 2).to(dev)
+    vals = torch.randn(N, generator=gen).to(dev)
+    actions = torch.randint(0, A, (N,), generator=gen).to(dev)
+    advs = torch.randn(N, generator=gen).to(dev)
+    rets = torch.randn(N, generator=gen).to(dev)
+    hyps = dict(pi_coef=1.0, val_coef=0.5, entr_coef=0.005, norm_advs=True, use_nstep_rets=False)
+    stats = torch.stack([advs.double().sum(), (advs.double() ** 2).sum()])
+    dl, dv, out = ops.loss_fwd_bwd(logits, vals, actions, advs, rets, stats, hyps)
+    parts = []
+    for sl in (slice(0, cut), slice(cut, N)):
+        parts.append(ops.loss_fwd_bwd(logits[sl].contiguous(), vals[sl].contiguous(),
+                                      actions[sl].contiguous(), advs[sl].contiguous(),
+                                      rets[sl].contiguous(), stats, hyps, n_global=N))
+    assert H.rel_err(torch.cat([p[0] for p in parts]).cpu().numpy(), dl.cpu().numpy()) < 1e-6
+    assert H.rel_err(torch.cat([p[1] for p in parts]).cpu().numpy(), dv.cpu().numpy()) < 1e-6
+    assert H.rel_err((parts[0][2] + parts[1][2]).cpu().numpy(), out.cpu().numpy()) < TOL
+
+
 # ---------------------------------------------------------------- stage 4 ----
 
 @pytest.mark.parametrize("M,N,K,ta,tb", [
