@@ -1,0 +1,576 @@
+// Shift-GEMM convolutions on tcgen05: no im2col at all.
+//
+// A band of input rows is converted once (NCHW fp32 -> hi/lo TF32 split) into shared
+// memory in the "interleaved pixel layout"
+//      element (channel group g, position q, channel c&3)  at  g*PLANE + q*16 + (c&3)*4  bytes
+// where q = row*PW + col runs over the zero-padded band.  In that layout the 128 x 8 operand
+// of  D[position, co] += X[position + shift(tap), ci] * W[tap][co][ci]  for ANY tap is just the
+// band itself read through a no-swizzle K-major UMMA descriptor (8 positions x 16 B core
+// matrices, SBO = 128 B, LBO = PLANE) whose start address is advanced by shift(tap)*16 bytes.
+// So every input element is loaded, split and stored once and each tap is a descriptor add --
+// the MMA warp issues  taps x (C/8) x 3  instructions per 128 output positions, nothing else
+// touches the operand.  Output positions are enumerated in the PADDED row pitch PW (the few
+// columns >= the real width are computed and dropped), which is what makes a tap a pure shift.
+//
+//   stride-2 forward : the band is stored as 4 parity planes (y&1, x&1); tap (ky,kx) reads
+//                      plane (ky&1, kx&1) at shift (ky>>1, kx>>1)
+//   backward-data    : one pass per output parity class over the dY band (stride-1
+//                      correlation with the taps of that class); the ReLU mask of the layer
+//                      (Ymask > 0) is applied while the band is converted, so the masked
+//                      gradient never exists in HBM
+//
+// Weights for all taps stay resident in shared memory (hi/lo).  TMEM accumulators add with
+// truncation (tc_core.cuh), so the taps of a tile are split into `nch` short chains that the
+// drain warps sum in fp32 registers.
+//
+// Replaces nn.Conv2d forward / input-gradient of a2c/models.py:98,312,685 for 3x3 pad-1 layers.
+#include <stdlib.h>
+
+#include <atomic>
+
+#include "tc_core.cuh"
+
+namespace a2c {
+extern std::atomic<long long> g_launches;
+
+namespace tc {
+
+constexpr int SH_MAXTAPS = 16;
+constexpr int SH_PROD = 12;                                   // producer warps
+constexpr int SH_NISS = 4;                                    // MMA issuer warps (tiles round-robin)
+constexpr int SH_DRAIN0 = SH_PROD, SH_MMA = SH_DRAIN0 + NUM_EPI_WARPS, SH_ALLOC = SH_MMA + SH_NISS;
+constexpr int SH_THREADS = 32 * (SH_ALLOC + 1);               // 25 warps
+constexpr int SH_MAXSLOT = 4;                                 // TMEM accumulator slots
+static_assert((SH_NISS & (SH_NISS - 1)) == 0, "issuer count must be a power of two");
+static_assert(SH_DRAIN0 % 4 == 0, "drain warps must start at a multiple of 4");
+
+struct ShiftTap {
+  uint32_t a_off16;       // class offset + shift, in positions (= 16-byte units)
+  uint32_t woff;          // offset of the tap inside one (n, k) weight slice
+};
+struct ShiftClass {       // one output parity class
+  int tap0, ntaps, a, b, qh, qw;
+};
+
+struct ShiftParams {
+  const float* src;       // f32 [N][C][SH][SW], SW % 4 == 0
+  const float* mask;      // optional, same shape: source element counts only where mask > 0
+  int N, C, SH, SW, ncg, ksteps;
+  int cs;                 // input class step (1, or 2 for the stride-2 forward)
+  int p0y, p0x;           // plane (row r, col c, class cy,cx) <-> source (r*cs + cy - p0y, c*cs + cx - p0x)
+  int PW;                 // class plane width
+  int rext_y[2];          // halo rows of the planes of class row cy
+  int cls_pos[4];         // first position of class (cy, cx) inside a channel-group plane
+  int plane_pos;          // positions per channel-group plane over all classes (multiple of 8)
+  int QH, Rb, nbands;     // band grid
+  int noc, os;            // output classes, output step
+  ShiftClass oc[4];
+  ShiftTap taps[SH_MAXTAPS];
+  int ntaps_total, nch;
+  const float* wt;        // W(n, k, tap) = wt[n*wsn + k*wsk + woff(tap)]
+  int wsn, wsk, J, n0;    // J output channels in total, this launch produces [n0, n0 + NPAD)
+  const float* bias;
+  int relu;
+  float* out;
+  int OutH, OutW;
+  int half_bytes, buf_bytes, w_half_bytes, nbuf;
+  int dbg;
+};
+
+// no-swizzle K-major descriptor: 8-row groups SBO bytes apart, the two 16-byte k chunks LBO apart
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+template <int NC>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr));
+}
+
+__host__ __device__ constexpr int tmem_cols_pow2(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+struct BandInfo {
+  int img, r0, rows, ntile;
+};
+__device__ __forceinline__ BandInfo band_info(const ShiftParams& p, int item) {
+  BandInfo b;
+  b.img = item / p.nbands;
+  const int bi = item - b.img * p.nbands;
+  b.r0 = bi * p.Rb;
+  b.rows = min(p.Rb, p.QH - b.r0);
+  b.ntile = (b.rows * p.PW + TM - 1) / TM;
+  return b;
+}
+
+__device__ __forceinline__ void store_split(uint8_t* dst, int half_bytes, float a, float b, float c, float d) {
+  const float4 h = make_float4(tf32_rna(a), tf32_rna(b), tf32_rna(c), tf32_rna(d));
+  *reinterpret_cast<float4*>(dst) = h;
+  *reinterpret_cast<float4*>(dst + half_bytes) = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_constant__ ShiftParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int NCOL = NPAD / 2;                      // accumulator columns per drain warp
+  constexpr int LDN = NCOL >= 16 ? 16 : 8;
+  constexpr int WBLK = NPAD * 32;                     // bytes of one (tap, kstep) weight block
+  uint8_t* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* wsm = base;                                // [hi | lo] x [tap][kstep][kchunk][n][4]
+  uint8_t* bufs = wsm + 2 * p.w_half_bytes;           // nbuf band buffers, each [hi | lo][cg][class][pos][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bufs + (size_t)p.nbuf * p.buf_bytes + 4096);  // 4 KB overrun slack
+  uint64_t* patch_full = bars;                        // [2]
+  uint64_t* patch_empty = bars + 2;                   // [2]
+  uint64_t* acc_full = bars + 4;                      // [SH_MAXSLOT]
+  uint64_t* acc_empty = bars + 4 + SH_MAXSLOT;        // [SH_MAXSLOT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * SH_MAXSLOT);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);   // [NPAD]
+
+  // shuffle-broadcast: tells the compiler the warp index (and everything derived from it) is
+  // warp-uniform, so role branches are uniform and the MMA loop can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int nitems = p.N * p.nbands;
+  // accumulator slots: a tile (nch chains of NPAD columns) per slot, tile i uses slot i % nslot
+  const uint32_t nslot = (SH_MAXSLOT * p.nch * NPAD <= 512) ? SH_MAXSLOT : 2;
+  const uint32_t tcols = (uint32_t)tmem_cols_pow2(nslot * p.nch * NPAD);
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&patch_full[b], SH_PROD);
+      mbar_init(&patch_empty[b], SH_NISS);
+    }
+    for (int b = 0; b < SH_MAXSLOT; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], NUM_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == SH_ALLOC) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tcols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // resident weights: block (tap g, kstep ks) = [kchunk][n][4], k = ks*8 + kchunk*4 + e
+  {
+    const int units = p.ntaps_total * p.ksteps * 2 * NPAD;
+    for (int u = threadIdx.x; u < units; u += SH_THREADS) {
+      const int n = u % NPAD;
+      int r = u / NPAD;
+      const int kc = r & 1;
+      r >>= 1;
+      const int ks = r % p.ksteps, g = r / p.ksteps;
+      float v[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = ks * 8 + kc * 4 + e;
+        v[e] = (p.n0 + n < p.J) ? __ldg(p.wt + (long long)(p.n0 + n) * p.wsn + (long long)k * p.wsk + p.taps[g].woff)
+                                : 0.0f;
+      }
+      store_split(wsm + (size_t)(g * p.ksteps + ks) * WBLK + kc * (NPAD * 16) + n * 16, p.w_half_bytes, v[0], v[1],
+                  v[2], v[3]);
+    }
+    for (int n = threadIdx.x; n < NPAD; n += SH_THREADS)
+      bias_s[n] = (p.bias && p.n0 + n < p.J) ? __ldg(p.bias + p.n0 + n) : 0.0f;
+    // the pad columns of the planes are never written by the producers: clear the buffers once
+    const int nz = p.nbuf * p.buf_bytes / 16;
+    for (int i = threadIdx.x; i < nz; i += SH_THREADS) reinterpret_cast<uint4*>(bufs)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp < SH_PROD) {
+    // ---------------- producers: source band -> interleaved hi/lo planes ----------------
+    // A lane converts 4 consecutive pixels of 4 channels: 4 LDG.128 in, the 4x4 block is
+    // transposed in registers (free) and leaves as 4 + 4 STS.128 (hi, lo).  A source row is
+    // NX4 float4 wide, so 32 / NX4 (row, channel group) tasks share a warp.
+    const int NX4 = p.SW >> 2;
+    const int tpw = 32 / NX4;                                  // tasks per warp pass
+    const int sub = lane / NX4, m = lane - sub * NX4;
+    const bool lane_on = sub < tpw;
+    const int plane = p.SH * p.SW;                             // elements per channel
+    StageRing ring(p.nbuf);
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ring.next()) {
+      const BandInfo bd = band_info(p, item);
+      uint8_t* buf = bufs + (size_t)ring.s * p.buf_bytes;
+      mbar_wait_relaxed(&patch_empty[ring.s], ring.par ^ 1);   // long wait: do not burn issue slots
+      const float4* simg = reinterpret_cast<const float4*>(p.src + (long long)bd.img * p.C * plane);
+      const float4* mimg = p.mask ? reinterpret_cast<const float4*>(p.mask + (long long)bd.img * p.C * plane) : nullptr;
+      for (int cy = 0; cy < p.cs && !(p.dbg & 4); ++cy) {
+        const int ntask = (bd.rows + p.rext_y[cy]) * p.ncg;    // (r, cg)
+        for (int task = warp * tpw + sub; task < ntask; task += SH_PROD * tpw) {
+          if (!lane_on) continue;
+          const int r = task / p.ncg, cg = task - r * p.ncg;
+          const int sy = (bd.r0 + r) * p.cs + cy - p.p0y;
+          const bool rowok = (unsigned)sy < (unsigned)p.SH;
+          const int e0 = (rowok ? (cg * 4 * plane + sy * p.SW) >> 2 : 0) + m;   // float4 index, channel 0
+          const int pl4 = rowok ? plane >> 2 : 0;
+          float4 v0 = __ldg(simg + e0), v1 = __ldg(simg + e0 + pl4), v2 = __ldg(simg + e0 + 2 * pl4),
+                 v3 = __ldg(simg + e0 + 3 * pl4);
+          if (mimg) {
+            const float4 m0 = __ldg(mimg + e0), m1 = __ldg(mimg + e0 + pl4), m2 = __ldg(mimg + e0 + 2 * pl4),
+                         m3 = __ldg(mimg + e0 + 3 * pl4);
+            v0.x = m0.x > 0.f ? v0.x : 0.f; v0.y = m0.y > 0.f ? v0.y : 0.f; v0.z = m0.z > 0.f ? v0.z : 0.f; v0.w = m0.w > 0.f ? v0.w : 0.f;
+            v1.x = m1.x > 0.f ? v1.x : 0.f; v1.y = m1.y > 0.f ? v1.y : 0.f; v1.z = m1.z > 0.f ? v1.z : 0.f; v1.w = m1.w > 0.f ? v1.w : 0.f;
+            v2.x = m2.x > 0.f ? v2.x : 0.f; v2.y = m2.y > 0.f ? v2.y : 0.f; v2.z = m2.z > 0.f ? v2.z : 0.f; v2.w = m2.w > 0.f ? v2.w : 0.f;
+            v3.x = m3.x > 0.f ? v3.x : 0.f; v3.y = m3.y > 0.f ? v3.y : 0.f; v3.z = m3.z > 0.f ? v3.z : 0.f; v3.w = m3.w > 0.f ? v3.w : 0.f;
+          }
+          if (!rowok) v0 = v1 = v2 = v3 = make_float4(0.f, 0.f, 0.f, 0.f);
+          uint8_t* dst = buf + ((size_t)cg * p.plane_pos + r * p.PW) * 16;
+          const int xq = 4 * m + p.p0x;                        // plane x' of pixel 0
+          if (p.cs == 1) {
+            dst += (size_t)(p.cls_pos[0] + xq) * 16;
+            store_split(dst, p.half_bytes, v0.x, v1.x, v2.x, v3.x);
+            store_split(dst + 16, p.half_bytes, v0.y, v1.y, v2.y, v3.y);
+            store_split(dst + 32, p.half_bytes, v0.z, v1.z, v2.z, v3.z);
+            store_split(dst + 48, p.half_bytes, v0.w, v1.w, v2.w, v3.w);
+          } else {
+            const int* cp = p.cls_pos + cy * 2;
+            store_split(dst + (size_t)(cp[xq & 1] + (xq >> 1)) * 16, p.half_bytes, v0.x, v1.x, v2.x, v3.x);
+            store_split(dst + (size_t)(cp[(xq + 1) & 1] + ((xq + 1) >> 1)) * 16, p.half_bytes, v0.y, v1.y, v2.y, v3.y);
+            store_split(dst + (size_t)(cp[xq & 1] + ((xq + 2) >> 1)) * 16, p.half_bytes, v0.z, v1.z, v2.z, v3.z);
+            store_split(dst + (size_t)(cp[(xq + 1) & 1] + ((xq + 3) >> 1)) * 16, p.half_bytes, v0.w, v1.w, v2.w, v3.w);
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&patch_full[ring.s]);
+    }
+  } else if (warp >= SH_MMA && warp < SH_MMA + SH_NISS) {
+    // Several issuer warps: one warp sustains roughly one small tcgen05.mma per ~100 cycles when
+    // its operands go through vector registers; the loop below lives entirely in uniform
+    // registers (about 3 instructions per MMA) and tiles are dealt round-robin to SH_NISS warps.
+    const uint32_t me = (uint32_t)(warp - SH_MMA);
+    constexpr uint32_t idesc = make_idesc(NPAD);
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);    // SBO = 128 B, descriptor version 1
+    const uint32_t a_w0 = (uint32_t)make_desc_nosw(smem_u32(bufs), (uint32_t)p.plane_pos * 16u, 128);
+    const uint32_t b_w0 = (uint32_t)make_desc_nosw(smem_u32(wsm), NPAD * 16, 128);
+    // 32-bit arithmetic on the low descriptor word only (address >> 4 in bits 0-13, no carry out)
+    const uint32_t buf16 = (uint32_t)p.buf_bytes >> 4, half16 = (uint32_t)p.half_bytes >> 4;
+    const uint32_t wlo16 = (uint32_t)p.w_half_bytes >> 4;
+    const uint32_t kstep16 = 2u * (uint32_t)p.plane_pos;      // 8 channels = 2 channel-group planes
+    StageRing ring(p.nbuf);
+    uint32_t tcount = 0, slot = 0, sphase = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ring.next()) {
+      const BandInfo bd = band_info(p, item);
+      mbar_wait(&patch_full[ring.s], ring.par);
+      tc_fence_after();
+      const uint32_t a_buf = a_w0 + ring.s * buf16;
+      for (int oc = 0; oc < p.noc; ++oc) {
+        const int tpc = p.oc[oc].ntaps / p.nch;
+        for (int t = 0; t < bd.ntile; ++t, ++tcount) {
+          const uint32_t ab = slot, aphase = sphase;
+          if (++slot == nslot) { slot = 0; sphase ^= 1u; }
+          if ((tcount & (SH_NISS - 1)) != me) continue;
+          mbar_wait(&acc_empty[ab], aphase ^ 1u);
+          tc_fence_after();
+          if (!(p.dbg & 2) && elect_one()) {
+            int g = p.oc[oc].tap0;
+            for (int ch = 0; ch < p.nch; ++ch) {
+              const uint32_t tmem_d = tmem_base + (ab * p.nch + ch) * NPAD;
+              uint32_t acc = 0;
+              for (int tp = 0; tp < tpc; ++tp, ++g) {
+                uint32_t a_hi = a_buf + p.taps[g].a_off16 + (uint32_t)(t * TM);
+                uint32_t b_hi = b_w0 + (uint32_t)(g * p.ksteps) * (WBLK >> 4);
+                for (int ks = 0; ks < p.ksteps; ++ks) {
+                  mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + half16, b_hi, acc);
+                  mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi, b_hi + wlo16, 1u);
+                  mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi, b_hi, 1u);
+                  acc = 1u;
+                  a_hi += kstep16;
+                  b_hi += (WBLK >> 4);
+                }
+              }
+            }
+          }
+          __syncwarp();
+          if (elect_one()) mma_commit(&acc_full[ab]);
+        }
+      }
+      if (elect_one()) mma_commit(&patch_empty[ring.s]);
+    }
+  } else if (warp >= SH_DRAIN0 && warp < SH_DRAIN0 + NUM_EPI_WARPS) {
+    // 8 warps per tile: TMEM lane quarter q, column half hsel.  The SM is issue-bound, so the
+    // loop is kept lean: incremental (row, col) of the lane's position, 32-bit store offsets.
+    const int e = warp - SH_DRAIN0, q = e & 3, hsel = e >> 2;
+    const int row = q * 32 + lane;
+    const int col0 = hsel * NCOL;
+    const int plane = p.OutH * p.OutW;
+    const int nvalid = min(NCOL, p.J - p.n0 - col0);
+    const float floor_v = p.relu ? 0.0f : -INFINITY;
+    const float4* bias4 = reinterpret_cast<const float4*>(bias_s + col0);
+    const int q128 = TM / p.PW, r128 = TM - q128 * p.PW;     // position step of one tile in (row, col)
+    const int jr0 = row / p.PW, i0 = row - jr0 * p.PW;
+    uint32_t slot = 0, sphase = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const BandInfo bd = band_info(p, item);
+      float* oimg = p.out + ((long long)bd.img * p.J + p.n0 + col0) * plane;
+      for (int oc = 0; oc < p.noc; ++oc) {
+        const ShiftClass c = p.oc[oc];
+        int jr = jr0, i = i0;
+        for (int t = 0; t < bd.ntile; ++t) {
+          const uint32_t ab = slot;
+          mbar_wait(&acc_full[ab], sphase);
+          if (++slot == nslot) { slot = 0; sphase ^= 1u; }
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.nch * NPAD + col0;
+          float acc[NCOL];
+          if (NCOL <= 16 && p.nch == 3) {
+            // all three chains in flight, one wait
+            uint32_t r0[NCOL], r1[NCOL], r2[NCOL];
+            tmem_ld<LDN>(taddr, r0);
+            tmem_ld<LDN>(taddr + NPAD, r1);
+            tmem_ld<LDN>(taddr + 2 * NPAD, r2);
+            if (NCOL > LDN) {
+              tmem_ld<LDN>(taddr + LDN, r0 + NCOL - LDN);
+              tmem_ld<LDN>(taddr + NPAD + LDN, r1 + NCOL - LDN);
+              tmem_ld<LDN>(taddr + 2 * NPAD + LDN, r2 + NCOL - LDN);
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int jj = 0; jj < NCOL; ++jj)
+              acc[jj] = (__uint_as_float(r0[jj]) + __uint_as_float(r1[jj])) + __uint_as_float(r2[jj]);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < NCOL; ++jj) acc[jj] = 0.0f;
+            for (int ch = 0; ch < p.nch; ++ch) {
+              uint32_t r[NCOL];
+#pragma unroll
+              for (int c0 = 0; c0 < NCOL; c0 += LDN) tmem_ld<LDN>(taddr + ch * NPAD + (uint32_t)c0, r + c0);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int jj = 0; jj < NCOL; ++jj) acc[jj] += __uint_as_float(r[jj]);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[ab]);
+          const int j = bd.r0 + jr;
+          if (jr < bd.rows && j < c.qh && i < c.qw && !(p.dbg & 8)) {
+            int idx = (j * p.os + c.a) * p.OutW + i * p.os + c.b;
+#pragma unroll
+            for (int j4 = 0; j4 < NCOL / 4; ++j4) {
+              const float4 b4 = bias4[j4];
+              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                if (j4 * 4 + u < nvalid) oimg[idx] = fmaxf(acc[j4 * 4 + u] + bb[u], floor_v);
+                idx += plane;
+              }
+            }
+          }
+          jr += q128; i += r128;
+          if (i >= p.PW) { i -= p.PW; ++jr; }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == SH_ALLOC) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tcols));
+  }
+}
+
+// ---------------------------------------------------------------------------- host side ----------
+static constexpr int SH_SMEM_LIMIT = 227 * 1024;
+
+static size_t shift_smem_bytes(const ShiftParams& p) {
+  return 2 * (size_t)p.w_half_bytes + (size_t)p.nbuf * p.buf_bytes + 4096 + 128 + 512;
+}
+
+// positions of one channel-group plane for bands of rb rows; fills cls_pos
+static int shift_plane_pos(ShiftParams* p, int rb) {
+  int pos = 0;
+  for (int cy = 0; cy < p->cs; ++cy)
+    for (int cx = 0; cx < p->cs; ++cx) {
+      p->cls_pos[cy * p->cs + cx] = pos;
+      pos += (rb + p->rext_y[cy]) * p->PW;
+    }
+  return (pos + 7) & ~7;
+}
+
+// Chooses band height and buffer count; false when the layer does not fit.
+static bool shift_plan(ShiftParams* p, int npad) {
+  p->w_half_bytes = p->ntaps_total * p->ksteps * npad * 32;
+  for (int nbuf = 2; nbuf >= 1; --nbuf) {
+    const long long avail = (long long)SH_SMEM_LIMIT - 2LL * p->w_half_bytes - 4096 - 640;
+    if (avail <= 0) return false;
+    int rb = 0;
+    for (int cand = p->QH; cand >= 1; --cand)
+      if (2LL * p->ncg * shift_plane_pos(p, cand) * 16 * nbuf <= avail) { rb = cand; break; }
+    if (rb < 1) continue;
+    if (nbuf == 2 && rb < 2 && p->QH > 1) continue;     // a one-row band is mostly halo: single buffer instead
+    const int nb = cdiv(p->QH, rb);
+    rb = cdiv(p->QH, nb);
+    p->Rb = rb; p->nbands = nb; p->nbuf = nbuf;
+    p->plane_pos = shift_plane_pos(p, rb);
+    p->half_bytes = p->ncg * p->plane_pos * 16;
+    p->buf_bytes = 2 * p->half_bytes;
+    if (shift_smem_bytes(*p) <= (size_t)SH_SMEM_LIMIT && p->plane_pos * 16 < (1 << 18)) return true;
+  }
+  return false;
+}
+
+template <int NPAD>
+static int shift_launch(ShiftParams& p, cudaStream_t st) {
+  auto kern = conv_shift_kernel<NPAD>;
+  static bool configured = false;
+  if (!configured) {
+    A2C_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_LIMIT));
+    configured = true;
+  }
+  const int nitems = p.N * p.nbands;
+  int grid = num_sms();
+  if (grid > nitems) grid = nitems;
+  kern<<<grid, SH_THREADS, shift_smem_bytes(p), st>>>(p);
+  g_launches++;
+  A2C_LAUNCH_CHECK();
+  return 0;
+}
+
+static int floordiv_i(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+}  // namespace tc
+
+using tc::ShiftParams;
+
+static bool shift_enabled() {
+  static const bool off = getenv("A2C_NO_SHIFT") != nullptr;
+  return !off;
+}
+
+// Tries output-channel chunks of 64 / 32 / 16 (the resident weights must leave room for the
+// bands), fills the tap table for the resulting plan and launches one kernel per chunk.
+template <class FillTaps>
+static int shift_run(ShiftParams& p, FillTaps fill, cudaStream_t st) {
+  const int cands[3] = {64, 32, 16};
+  for (int ci = 0; ci < 3; ++ci) {
+    const int npad = cands[ci];
+    if (npad >= 2 * p.J && npad > 16) continue;                 // do not pad a narrow layer to a wide tile
+    if (2 * p.nch * npad > 512) continue;                       // TMEM columns
+    if ((long long)p.ntaps_total * p.ksteps * npad * 64 > 80 * 1024 && npad > 16) continue;
+    if (!tc::shift_plan(&p, npad)) continue;
+    if (!fill(p)) return 1;
+    { const char* e = getenv("A2C_SHIFT_DBG"); p.dbg = e ? atoi(e) : 0; }
+    if (p.dbg & 64) p.nch = 1;
+    for (int n0 = 0; n0 < p.J; n0 += npad) {
+      p.n0 = n0;
+      int rc = npad == 64 ? tc::shift_launch<64>(p, st) : npad == 32 ? tc::shift_launch<32>(p, st)
+                                                                     : tc::shift_launch<16>(p, st);
+      if (rc) return rc;
+    }
+    return 0;
+  }
+  return 1;
+}
+
+// 0 = ran, 1 = not supported (caller falls back), else error
+int conv_fwd_shift_try(const float* X, const float* Wt, const float* bias, float* Y, int N,
+                       const a2c_conv_shape* s, int relu, cudaStream_t st) {
+  const int K = s->K, S = s->stride, P = s->pad;
+  if (!shift_enabled() || !X || K != 3 || P != 1 || (S != 1 && S != 2) || (s->Cin % 8) != 0) return 1;
+  if ((S == 2 && ((s->H | s->W) & 1)) || s->Cout > 128) return 1;
+  static thread_local ShiftParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = X; p.N = N; p.C = s->Cin; p.SH = s->H; p.SW = s->W; p.ncg = s->Cin / 4; p.ksteps = s->Cin / 8;
+  // source (y, x) lives in parity plane ((y+P) % S, (x+P) % S) at ((y+P) / S, (x+P) / S); tap
+  // (ky, kx) of output (oy, ox) reads plane (ky % S, kx % S) at (oy + ky / S, ox + kx / S)
+  p.cs = S; p.p0y = P; p.p0x = P;
+  p.PW = s->OW + (K - 1) / S;
+  for (int cy = 0; cy < S; ++cy) p.rext_y[cy] = (K - 1 - cy) / S;
+  if ((s->W & 3) || s->W > 128 || (reinterpret_cast<uintptr_t>(X) & 15)) return 1;
+  p.QH = s->OH; p.noc = 1; p.os = 1;
+  p.oc[0] = {0, K * K, 0, 0, s->OH, s->OW};
+  p.ntaps_total = K * K; p.nch = K;                 // one accumulator chain per kernel row
+  p.wt = Wt; p.wsn = s->Cin * K * K; p.wsk = K * K; p.J = s->Cout; p.bias = bias; p.relu = relu;
+  p.out = Y; p.OutH = s->OH; p.OutW = s->OW;
+  return shift_run(p, [K, S](ShiftParams& q) {
+    for (int ky = 0; ky < K; ++ky)
+      for (int kx = 0; kx < K; ++kx) {
+        const int g = ky * K + kx, cls = (ky % S) * S + (kx % S);
+        q.taps[g].a_off16 = (uint32_t)(q.cls_pos[cls] + (ky / S) * q.PW + (kx / S));
+        q.taps[g].woff = (uint32_t)g;
+      }
+    return true;
+  }, st);
+}
+
+int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
+                         const a2c_conv_shape* s, cudaStream_t st) {
+  const int K = s->K, S = s->stride, P = s->pad;
+  if (!shift_enabled() || K != 3 || P != 1 || (S != 1 && S != 2) || (s->Cout % 8) != 0) return 1;
+  if ((S == 2 && ((s->H | s->W) & 1)) || s->Cin > 128) return 1;
+  static thread_local ShiftParams p;
+  memset(&p, 0, sizeof(p));
+  p.src = dY; p.mask = Ymask; p.N = N; p.C = s->Cout; p.SH = s->OH; p.SW = s->OW;
+  p.ncg = s->Cout / 4; p.ksteps = s->Cout / 8;
+  p.cs = 1;
+  // tap k contributes to dX row y = S*j + a from dY row j + d, d = (a + P - k) / S when divisible
+  int dmin = 0, dmax = 0;
+  for (int a = 0; a < S; ++a)
+    for (int k = 0; k < K; ++k)
+      if (((a + P - k) % S + S) % S == 0) {
+        const int d = tc::floordiv_i(a + P - k, S);
+        dmin = d < dmin ? d : dmin;
+        dmax = d > dmax ? d : dmax;
+      }
+  p.p0y = -dmin; p.p0x = -dmin;
+  p.rext_y[0] = dmax - dmin;
+  p.PW = cdiv(s->W, S) + p.rext_y[0];
+  if ((s->OW & 3) || s->OW > 128 || (reinterpret_cast<uintptr_t>(dY) & 15) ||
+      (Ymask && (reinterpret_cast<uintptr_t>(Ymask) & 15)))
+    return 1;
+  p.QH = cdiv(s->H, S); p.noc = S * S; p.os = S;
+  p.nch = 1;
+  p.wt = Wt; p.wsn = K * K; p.wsk = s->Cin * K * K; p.J = s->Cin;
+  p.out = dX; p.OutH = s->H; p.OutW = s->W;
+  p.ntaps_total = K * K;
+  const int H = s->H, W = s->W;
+  return shift_run(p, [K, S, P, H, W, dmin](ShiftParams& q) {
+    int g = 0;
+    for (int a = 0; a < S; ++a)
+      for (int b = 0; b < S; ++b) {
+        tc::ShiftClass& c = q.oc[a * S + b];
+        c.tap0 = g; c.a = a; c.b = b;
+        c.qh = (H - a + S - 1) / S; c.qw = (W - b + S - 1) / S;
+        for (int ky = 0; ky < K; ++ky) {
+          if (((a + P - ky) % S + S) % S != 0) continue;
+          for (int kx = 0; kx < K; ++kx) {
+            if (((b + P - kx) % S + S) % S != 0) continue;
+            const int dy = tc::floordiv_i(a + P - ky, S) - dmin, dx = tc::floordiv_i(b + P - kx, S) - dmin;
+            q.taps[g].a_off16 = (uint32_t)(dy * q.PW + dx);
+            q.taps[g].woff = (uint32_t)(ky * K + kx);
+            ++g;
+          }
+        }
+        c.ntaps = g - c.tap0;
+        if (c.ntaps == 0) return false;
+      }
+    return true;
+  }, st);
+}
+
+}  // namespace a2c

@@ -466,6 +466,12 @@ int conv_wgrad_tc_try(const float* X, const a2c_state_view* xview, const float* 
                       float* dbias, int N, const a2c_conv_shape* s, void* workspace,
                       long long workspace_bytes, int precision, cudaStream_t st);
 
+// conv_shift_tc.cu (3xTF32 only): 3x3 pad-1 layers as shifted-descriptor GEMMs, no im2col
+int conv_fwd_shift_try(const float* X, const float* Wt, const float* bias, float* Y, int N,
+                       const a2c_conv_shape* s, int relu, cudaStream_t st);
+int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
+                         const a2c_conv_shape* s, cudaStream_t st);
+
 int conv_fwd_patch_try(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias,
                        float* Y, int N, const a2c_conv_shape* s, int relu, int precision, cudaStream_t st);
 int conv_dgrad_patch_try(const float* dY, const float* Wt, float* dX, int N, const a2c_conv_shape* s,
@@ -491,7 +497,9 @@ int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
   // {0,1}-valued input layer identical to the reference's.
   if (precision != 0 && s->Cin > 4) {
     A2C_ARG_CHECK(xview || X, "conv_fwd: null input");
-    int rc = conv_fwd_patch_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
+    int rc = (precision == 1 && !xview) ? conv_fwd_shift_try(X, Wt, bias, Y, N, s, relu, as_stream(stream)) : 1;
+    if (rc != 1) return rc;
+    rc = conv_fwd_patch_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
     if (rc != 1) return rc;
     rc = conv_fwd_tc_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
     if (rc != 1) return rc;
@@ -508,6 +516,10 @@ int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, fl
   if (int rc = check_shape(s)) return rc;
   A2C_ARG_CHECK(dY && Wt && dX && N >= 0, "conv_bwd_data: bad args");
   if (N == 0) return 0;
+  if (precision == 1) {
+    int rc = conv_dgrad_shift_try(dY, Ymask, Wt, dX, N, s, as_stream(stream));
+    if (rc != 1) return rc;
+  }
   if (precision != 0 && !Ymask) {
     int rc = conv_dgrad_patch_try(dY, Wt, dX, N, s, precision, as_stream(stream));
     if (rc != 1) return rc;

@@ -66,10 +66,55 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 
+// Same instruction with the descriptors given as 32-bit halves: only the low word (start
+// address, LBO) changes inside a kernel, so issue loops can do 32-bit (uniform-register)
+// arithmetic on it and leave the constant high word (SBO, version, swizzle) alone.
+__device__ __forceinline__ void mma_tf32_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                           uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Variant for issue-bound loops: the instruction descriptor and the constant high descriptor
+// word are immediates (ptxas keeps them in uniform registers instead of re-materialising them
+// through R2UR for every instruction); only the low descriptor words are register operands.
+template <uint32_t IDESC, uint32_t DESC_HI>
+__device__ __forceinline__ void mma_tf32_imm(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t.reg .b32 hi, id;\n\t"
+      "setp.ne.b32 p, %3, 0;\n\t"
+      "mov.b32 hi, %4;\n\t"
+      "mov.b32 id, %5;\n\t"
+      "mov.b64 da, {%1, hi};\n\t"
+      "mov.b64 db, {%2, hi};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, id, p;\n\t}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(accumulate), "n"(DESC_HI), "n"(IDESC)
+      : "memory");
+}
+
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
                : "memory");
+}
+
+// One lane of a converged warp, chosen by the hardware (elect.sync): unlike `lane == 0` the
+// compiler knows exactly one thread is active in the guarded region, so a tcgen05.mma inside it
+// takes its (warp-uniform) operands straight from uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ float tf32_rna(float x) {
@@ -140,7 +185,8 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
   uint64_t* acc_empty = acc_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shuffle-broadcast marks the warp index as warp-uniform for the compiler (uniform role branches)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
   // persistent over m tiles: this CTA owns tiles blockIdx.y, blockIdx.y + gridDim.y, ...
   const int kb_begin = blockIdx.z * p.kb_per_split;
@@ -169,7 +215,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   auto stage_ptr = [&](int s) { return smem + s * STAGE_BYTES; };
   // stage layout: [A_hi][A_lo?][B_hi][B_lo?]
@@ -242,22 +288,26 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
       }
       mbar_wait(&full[s], parity);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t tmem_d = tmem_base + buf * BN;
-        const uint32_t a_hi = smem_u32(stage_ptr(s));
-        const uint32_t a_lo = a_hi + A_BYTES;
-        const uint32_t b_hi = a_hi + (SPLIT3 ? 2 : 1) * A_BYTES;
-        const uint32_t b_lo = b_hi + B_BYTES;
+      // convergent warp, one elected lane, descriptor low words in uniform registers (see
+      // mma_tf32_imm): about 3 issue instructions per MMA instead of ~25
+      constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
+      constexpr uint32_t LBO1 = 1u << 16;
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      const uint32_t a_hi = ((smem_u32(stage_ptr(s)) & 0x3FFFFu) >> 4) | LBO1;
+      const uint32_t a_lo = a_hi + (A_BYTES >> 4);
+      const uint32_t b_hi = a_hi + (((SPLIT3 ? 2 : 1) * A_BYTES) >> 4);
+      const uint32_t b_lo = b_hi + (B_BYTES >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < KB / 8; ++kk) {
-          const uint32_t koff = kk * 32;     // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+          const uint32_t koff = kk * 2;      // 8 tf32 = 32 bytes inside the 128-byte swizzle row
           const uint32_t first = ((i % KC) | kk) ? 1u : 0u;
           if constexpr (SPLIT3) {
-            mma_tf32(tmem_d, make_desc(a_lo + koff), make_desc(b_hi + koff), idesc, first);
-            mma_tf32(tmem_d, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1u);
-            mma_tf32(tmem_d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, 1u);
+            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_lo + koff, b_hi + koff, first);
+            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + koff, b_lo + koff, 1u);
+            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + koff, b_hi + koff, 1u);
           } else {
-            mma_tf32(tmem_d, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
+            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + koff, b_hi + koff, first);
           }
         }
         mma_commit(&empty[s]);                                   // frees the stage when these MMAs retire
