@@ -180,6 +180,11 @@ int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
  * output whose ReLU gates dY. */
 int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
                         const a2c_conv_shape* s, int precision, void* stream);
+/* Which backward entries apply the ReLU mask (Ymask > 0) themselves on the path they take for
+ * this shape / precision: bit 0 = a2c_conv2d_bwd_data, bit 1 = a2c_conv2d_bwd_weight.  A caller
+ * holding an unmasked dY passes Ymask to those and pre-masks dY (a2c_relu_bwd) for the others;
+ * passing Ymask to an entry whose bit is clear is still correct but runs the fp32 FFMA kernel. */
+int a2c_conv2d_fused_mask(const a2c_conv_shape* s, int precision, int input_is_view);
 /* dW, dbias from X (or xview) and dY * (Ymask > 0).  workspace >=
  * a2c_conv2d_bwd_weight_workspace(s) bytes. */
 long long a2c_conv2d_bwd_weight_workspace(const a2c_conv_shape* s);

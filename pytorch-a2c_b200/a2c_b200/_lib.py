@@ -64,6 +64,7 @@ SIGNATURES = {
     "a2c_relu_bwd": [_p, _p, _p, _ll, _p],
     "a2c_conv2d_fwd": [_p, _SV, _p, _p, _p, _i, _CS, _i, _i, _p],
     "a2c_conv2d_bwd_data": [_p, _p, _p, _p, _i, _CS, _i, _p],
+    "a2c_conv2d_fused_mask": [_CS, _i, _i],
     "a2c_conv2d_bwd_weight_workspace": [_CS],
     "a2c_conv2d_bwd_weight": [_p, _SV, _p, _p, _p, _p, _i, _CS, _p, _ll, _i, _p],
     "a2c_layernorm_fwd": [_p, _p, _p, _p, _p, _p, _ll, _i, _p],
@@ -78,7 +79,7 @@ SIGNATURES = {
 _RESTYPES = {"a2c_last_error": C.c_char_p, "a2c_launch_count": C.c_longlong,
              "a2c_conv2d_bwd_weight_workspace": C.c_longlong}
 _NO_STATUS = {"a2c_abi_version", "a2c_last_error", "a2c_launch_count",
-              "a2c_conv2d_bwd_weight_workspace"}
+              "a2c_conv2d_bwd_weight_workspace", "a2c_conv2d_fused_mask"}
 
 _lib = None
 

@@ -342,9 +342,15 @@ class Conv2dFn(torch.autograd.Function):
         dy = dy.contiguous()
         mask = y if ctx.relu else None
         prec = ctx.precision
-        if prec != 0 and mask is not None:
-            dy = relu_bwd(dy, y)       # the tensor-core kernels take the masked gradient
-            mask = None
+        need_dx = not ctx.is_view and ctx.needs_input_grad[0]
+        need_dw = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        if mask is not None:
+            # the shift-GEMM kernels apply the ReLU mask while they stage dY; the other
+            # tensor-core paths want the masked gradient (one extra elementwise pass)
+            fused = call("a2c_conv2d_fused_mask", C.byref(s), prec, 1 if ctx.is_view else 0)
+            if (need_dx and not fused & 1) or (need_dw and not fused & 2):
+                dy = relu_bwd(dy, y)
+                mask = None
         dx = dW = db = None
         if not ctx.is_view and ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)

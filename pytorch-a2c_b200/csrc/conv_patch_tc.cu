@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_patch_fwd_kernel(const __gr
   constexpr int HALF = BN / 2;
   const int KC = p.kc;   // forward: 1 (activations feed ReLU masks: keep the truncating TMEM chains short)
   PatchSmem sm = carve(smem_raw, p, p.b_resident ? p.nkb * BPAIR : 0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int ntiles = p.N * p.tiles_y * p.tiles_x;
   const int nchunks = (p.nkb + KC - 1) / KC;
 
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_patch_fwd_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *sm.tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *sm.tmem_slot, 0);
   auto stage_ptr = [&](int s) { return sm.stages + (size_t)s * p.stage_bytes; };
 
   if (warp < PW1) {
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_patch_wgrad_kernel(const __
   constexpr int KC = 1;                       // shortest TMEM chains: truncation is a bias (tc_core.cuh)
   constexpr int KBT = (PT_TH * PT_TW) / KB;   // 4 k-blocks (of 32 positions) per spatial tile
   PatchSmem sm = carve(smem_raw, p, 0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int ntiles = p.N * p.tiles_y * p.tiles_x;
   const int m0 = blockIdx.x * TM;             // first tap row of this CTA
   int my_tiles = 0;
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_patch_wgrad_kernel(const __
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *sm.tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *sm.tmem_slot, 0);
   auto stage_ptr = [&](int s) { return sm.stages + (size_t)s * STAGE_BYTES; };
 
   if (warp < PW1) {
@@ -620,44 +620,45 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_patch_wgrad_kernel(const __
       tile = ntile; q = nq; ring.next();
     }
   } else if (warp == P_MMA) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
-      const uint64_t a_desc0 = make_desc(smem_u32(sm.stages));
-      const uint32_t stage_step = (uint32_t)STAGE_BYTES >> 4;
-      StageRing ring(p.stages);
-      int chunk = 0, inchunk = 0;
-      for (int i = 0; i < nkb; ++i, ring.next()) {
-        const int buf = chunk & 1;
-        if (inchunk == 0) {
-          mbar_wait(&sm.acc_empty[buf], ((chunk >> 1) & 1) ^ 1);
-          tc_fence_after();
-        }
-        mbar_wait(&sm.full[ring.s], ring.par);
+    // convergent warp, one elected lane, descriptor low words in uniform registers (mma_tf32_imm)
+    constexpr uint32_t idesc = make_idesc(BN);
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
+    const uint32_t a_w0 = ((smem_u32(sm.stages) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t stage_step = (uint32_t)STAGE_BYTES >> 4;
+    StageRing ring(p.stages);
+    int chunk = 0, inchunk = 0;
+    for (int i = 0; i < nkb; ++i, ring.next()) {
+      const int buf = chunk & 1;
+      if (inchunk == 0) {
+        mbar_wait(&sm.acc_empty[buf], ((chunk >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * BN;
-        const uint64_t a_hi = a_desc0 + (uint64_t)(ring.s * stage_step);
-        const uint64_t a_lo = a_hi + (A_BYTES >> 4);
-        const uint64_t b_hi = a_hi + (((SPLIT3 ? 2 : 1) * A_BYTES) >> 4);
-        const uint64_t b_lo = b_hi + (B_BYTES >> 4);
+      }
+      mbar_wait(&sm.full[ring.s], ring.par);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      const uint32_t a_hi = a_w0 + ring.s * stage_step;
+      const uint32_t a_lo = a_hi + (A_BYTES >> 4);
+      const uint32_t b_hi = a_hi + (((SPLIT3 ? 2 : 1) * A_BYTES) >> 4);
+      const uint32_t b_lo = b_hi + (B_BYTES >> 4);
+      const bool last = (inchunk + 1 == KC) || (i == nkb - 1);
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < KB / 8; ++kk) {
-          const uint64_t ko = kk * 2;
+          const uint32_t ko = kk * 2;
           const uint32_t first = (inchunk | kk) ? 1u : 0u;
           if constexpr (SPLIT3) {
-            mma_tf32(tmem_d, a_lo + ko, b_hi + ko, idesc, first);
-            mma_tf32(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
-            mma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, 1u);
+            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_lo + ko, b_hi + ko, first);
+            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + ko, b_lo + ko, 1u);
+            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + ko, b_hi + ko, 1u);
           } else {
-            mma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, first);
+            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + ko, b_hi + ko, first);
           }
         }
         mma_commit(&sm.empty[ring.s]);
-        if (++inchunk == KC || i == nkb - 1) {
-          mma_commit(&sm.acc_full[buf]);
-          inchunk = 0;
-          ++chunk;
-        }
+        if (last) mma_commit(&sm.acc_full[buf]);
       }
+      __syncwarp();
+      if (last) { inchunk = 0; ++chunk; } else ++inchunk;
     }
   } else if (warp >= P_DRAIN0 && warp < P_DRAIN0 + NUM_EPI_WARPS) {
     const int e = warp - P_DRAIN0, q = e & 3, hsel = e >> 2;

@@ -518,11 +518,17 @@ int conv_fwd_shift_try(const float* X, const float* Wt, const float* bias, float
   }, st);
 }
 
+bool conv_dgrad_shift_ok(const a2c_conv_shape* s) {
+  const int S = s->stride;
+  if (!shift_enabled() || s->K != 3 || s->pad != 1 || (S != 1 && S != 2) || (s->Cout % 8) != 0) return false;
+  if ((S == 2 && ((s->H | s->W) & 1)) || s->Cin > 128) return false;
+  return (s->OW & 3) == 0 && s->OW <= 128;
+}
+
 int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
                          const a2c_conv_shape* s, cudaStream_t st) {
   const int K = s->K, S = s->stride, P = s->pad;
-  if (!shift_enabled() || K != 3 || P != 1 || (S != 1 && S != 2) || (s->Cout % 8) != 0) return 1;
-  if ((S == 2 && ((s->H | s->W) & 1)) || s->Cin > 128) return 1;
+  if (!conv_dgrad_shift_ok(s)) return 1;
   static thread_local ShiftParams p;
   memset(&p, 0, sizeof(p));
   p.src = dY; p.mask = Ymask; p.N = N; p.C = s->Cout; p.SH = s->OH; p.SW = s->OW;

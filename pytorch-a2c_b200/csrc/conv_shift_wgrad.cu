@@ -1,0 +1,502 @@
+// Shift-GEMM weight gradient of 3x3 pad-1 convolutions on tcgen05.
+//
+//   dW[co][ci][ky][kx] = sum over images and output positions of  X[ci][pos + shift(ky,kx)] * dY[co][pos]
+//
+// is a GEMM whose reduction (K) dimension is the output position.  Both operands are staged in
+// shared memory "position-major": one 128-byte row per position holding 32 channel slots, hi / lo
+// TF32 copies, 32-byte chunks XOR-swizzled by (row & 3) -- the SWIZZLE_128B_BASE32B layout, the
+// only one tcgen05 defines for MN-major 32-bit operands (the no-swizzle form returns zeros).
+// A k-step is 8 consecutive positions (= 8 rows, 1 KB); channel slots are the M / N extent.  A
+// tap is a shift of the X start address by whole rows, so there is no im2col and no transpose.
+//
+//   stride 1, Cin <= 16 : every X row also carries the channels of the image row below it in
+//                         slots [16, 32), so one 32-slot atom covers ky = 0, 1 and a second atom
+//                         two image rows further down covers ky = 2: M = 64, one MMA per kx.
+//   stride 1, Cin  > 16 : atoms of rows y, y+1, y+2 stack along M (M = 128).
+//   stride 2            : source rows are stored one after the other, each split into its two
+//                         x-parity planes; the atoms of rows 2oy-1, 2oy, 2oy+1 stack along M.
+// Image rows are processed in column chunks of <= 40 (stride 2: 20) positions so that two band
+// buffers fit.
+// dY is masked by the layer's ReLU (Ymask > 0) while it is converted.  The 3 kx accumulators
+// (3 x 32 TMEM columns) are chained over a few rows only (TMEM adds truncate, tc_core.cuh); the
+// drain warps keep running sums in fp32 registers and write one partial per CTA, reduced in
+// double afterwards.  The bias gradient is a masked per-channel sum in a separate small kernel.
+//
+// Replaces the weight / bias gradient of nn.Conv2d in a2c/models.py:98,312,685 (autograd).
+#include <stdlib.h>
+
+#include <atomic>
+
+#include "tc_core.cuh"
+
+namespace a2c {
+extern std::atomic<long long> g_launches;
+
+namespace tc {
+
+constexpr int WG_PROD = 12;
+constexpr int WG_NISS = 4;
+constexpr int WG_DRAIN0 = WG_PROD, WG_MMA = WG_DRAIN0 + NUM_EPI_WARPS, WG_ALLOC = WG_MMA + WG_NISS;
+constexpr int WG_THREADS = 32 * (WG_ALLOC + 1);
+constexpr int WG_NSLOT = 4;
+constexpr int WG_N = 32;                     // output channels per launch
+constexpr int WG_NACC = 3 * WG_N;            // TMEM columns of one accumulator set (kx = 0, 1, 2)
+constexpr int WG_ROWB = 128;                 // bytes of one position row (32 slots)
+static_assert(WG_DRAIN0 % 4 == 0, "drain warps must start at a multiple of 4");
+
+struct WgShiftParams {
+  const float* x;        // f32 [N][Cin][H][W]
+  const float* dy;       // f32 [N][Cout][OH][OW]
+  const float* mask;     // optional (layer output Y): dY counts only where mask > 0
+  int N, Cin, H, W, Cout, OH, OW;
+  int S;                 // stride
+  int pack2;             // stride 1, Cin <= 16: slots [16,32) = channels of the next image row
+  int ncx;               // x-parity planes per X row (1, or 2 for stride 2)
+  int OWc, ncol;         // output columns per chunk, chunks per row
+  int PWx, PWo;          // positions per X plane row / per dY row (PWo multiple of 8)
+  int xrows;             // source rows of a full band (Rb + 2 for stride 1, 2 Rb + 1 for stride 2)
+  int Rb, nbands, rpc;   // band height, bands per image, rows per accumulator chunk
+  int n0;                // first output channel of this launch
+  int mrows;             // MMA M (64 or 128)
+  int a_lbo;             // bytes between the M atoms of A
+  int x_half, x_buf;     // bytes of one hi copy / one buffer of the X band
+  int o_half, o_buf;     // same for the dY band
+  float* partial;        // [grid][128][WG_NACC]
+  int dbg;
+};
+
+// byte offset of 16-byte chunk j of the position row at byte address row_addr (bands 1024-byte aligned)
+__device__ __forceinline__ uint32_t wg_swz(uint32_t row_addr, int j) {
+  return ((((uint32_t)j >> 1) ^ ((row_addr >> 7) & 3u)) << 5) | (((uint32_t)j & 1u) << 4);
+}
+
+__device__ __forceinline__ void wg_store_split(uint8_t* dst, int half_bytes, float a, float b, float c, float d) {
+  const float4 h = make_float4(tf32_rna(a), tf32_rna(b), tf32_rna(c), tf32_rna(d));
+  *reinterpret_cast<float4*>(dst) = h;
+  *reinterpret_cast<float4*>(dst + half_bytes) = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);
+}
+
+__device__ __forceinline__ void wg_tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+struct WgItem {
+  int img, r0, rows, c0;          // image, first output row, rows, first output column of the chunk
+};
+
+// kind::tf32, fp32 accumulate, both operands MN-major
+__host__ __device__ constexpr uint32_t make_idesc_mn(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const __grid_constant__ WgShiftParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int NC = WG_NACC / 2;                      // accumulator columns per drain warp
+  uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* xb = base;                                  // 2 X buffers: [hi | lo][row][cx][c][32 slots]
+  uint8_t* ob = xb + 2 * p.x_buf;                      // 2 dY buffers: [hi | lo][row][c][32 slots]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ob + 2 * p.o_buf + 8192);   // 8 KB: over-read of junk M atoms
+  uint64_t* band_full = bars;                          // [2]
+  uint64_t* band_empty = bars + 2;                     // [2]
+  uint64_t* acc_full = bars + 4;                       // [WG_NSLOT]
+  uint64_t* acc_empty = bars + 4 + WG_NSLOT;           // [WG_NSLOT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4 + 2 * WG_NSLOT);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int first_item = (int)blockIdx.x, item_step = (int)gridDim.x;
+  const int per_img = p.nbands * p.ncol;
+  const int nitems = p.N * per_img;
+
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&band_full[b], WG_PROD);
+      mbar_init(&band_empty[b], WG_NISS);
+    }
+    for (int b = 0; b < WG_NSLOT; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], NUM_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == WG_ALLOC) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  {
+    // pad positions / pad slots are never written: clear both bands (and the over-read slack) once
+    const int nz = (2 * p.x_buf + 2 * p.o_buf + 8192) / 16;
+    for (int i = threadIdx.x; i < nz; i += WG_THREADS) reinterpret_cast<uint4*>(xb)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  auto item_of = [&](int item) {
+    WgItem it;
+    it.img = item / per_img;
+    int r = item - it.img * per_img;
+    const int bi = r / p.ncol;
+    it.c0 = (r - bi * p.ncol) * p.OWc;
+    it.r0 = bi * p.Rb;
+    it.rows = min(p.Rb, p.OH - it.r0);
+    return it;
+  };
+
+  if (warp < WG_PROD) {
+    // ---------------- producers ----------------
+    const int xplane = p.H * p.W, oplane = p.OH * p.OW;
+    const int ncgx = p.Cin >> 2;
+    StageRing ring(2);
+    for (int item = first_item; item < nitems; item += item_step, ring.next()) {
+      const WgItem it = item_of(item);
+      mbar_wait_relaxed(&band_empty[ring.s], ring.par ^ 1);
+      // --- X band.  A lane converts 4 consecutive pixels (one float4 per channel) of 4 channels. ---
+      {
+        uint8_t* buf = xb + (size_t)ring.s * p.x_buf;
+        const uint32_t buf_a = smem_u32(buf);
+        const float4* simg = reinterpret_cast<const float4*>(p.x + (long long)it.img * p.Cin * xplane);
+        // source columns needed: x in [xs, xe); covered by float4 groups g0 .. g0 + ng
+        const int xs = p.S == 1 ? it.c0 - 1 : 2 * it.c0 - 1;
+        const int xe = p.S == 1 ? it.c0 + p.OWc + 1 : 2 * (it.c0 + p.OWc);
+        const int g0 = (xs < 0 ? xs - 3 : xs) / 4;                 // floor(xs / 4)
+        const int ng = (xe + 3) / 4 - g0;
+        const int tpw = 32 / ng > 0 ? 32 / ng : 1;
+        const int sub = lane / ng, gi = lane - sub * ng;
+        const int nrow = p.S == 1 ? it.rows + 2 : 2 * it.rows + 1;     // source rows of the band
+        const int ntask = nrow * ncgx;
+        for (int task = warp * tpw + sub; task < ntask; task += WG_PROD * tpw) {
+          if (sub >= tpw) continue;
+          const int r = task / ncgx, cg = task - r * ncgx;
+          const int sy = p.S * it.r0 + r - 1;
+          const int x4 = 4 * (g0 + gi);
+          const bool ok = (unsigned)sy < (unsigned)p.H && (unsigned)x4 < (unsigned)p.W;
+          const int e0 = ok ? ((cg * 4 * xplane + sy * p.W + x4) >> 2) : 0;
+          const int pl4 = ok ? xplane >> 2 : 0;
+          float4 v0 = __ldg(simg + e0), v1 = __ldg(simg + e0 + pl4), v2 = __ldg(simg + e0 + 2 * pl4),
+                 v3 = __ldg(simg + e0 + 3 * pl4);
+          if (!ok) v0 = v1 = v2 = v3 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float px[4][4] = {{v0.x, v1.x, v2.x, v3.x}, {v0.y, v1.y, v2.y, v3.y},
+                                  {v0.z, v1.z, v2.z, v3.z}, {v0.w, v1.w, v2.w, v3.w}};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int xp = x4 + j - xs;                           // 0-based inside the needed range
+            if (xp < 0 || x4 + j >= xe) continue;
+            int prow, c;                                          // plane row, column inside it
+            if (p.S == 1) { prow = r; c = xp; }
+            else { prow = r * 2 + (xp & 1); c = xp >> 1; }        // x' = x + 1 = 2 * (c0 + c) + parity
+            const uint32_t off = (uint32_t)(prow * p.PWx + c) * WG_ROWB;
+            wg_store_split(buf + off + wg_swz(buf_a + off, cg), p.x_half, px[j][0], px[j][1], px[j][2], px[j][3]);
+            if (p.pack2 && r > 0) {                               // same pixel as the "row below" of the previous row
+              const uint32_t off2 = off - (uint32_t)p.PWx * WG_ROWB;
+              wg_store_split(buf + off2 + wg_swz(buf_a + off2, cg + 4), p.x_half, px[j][0], px[j][1], px[j][2],
+                             px[j][3]);
+            }
+          }
+        }
+      }
+      // --- dY band (masked) ---
+      {
+        uint8_t* buf = ob + (size_t)ring.s * p.o_buf;
+        const uint32_t buf_a = smem_u32(buf);
+        const float4* simg = reinterpret_cast<const float4*>(p.dy + ((long long)it.img * p.Cout + p.n0) * oplane);
+        const float4* mimg =
+            p.mask ? reinterpret_cast<const float4*>(p.mask + ((long long)it.img * p.Cout + p.n0) * oplane) : nullptr;
+        const int ng = p.OWc >> 2, tpw = 32 / ng;
+        const int sub = lane / ng, gi = lane - sub * ng;
+        const int ncg_valid = min(WG_N / 4, (p.Cout - p.n0) >> 2);
+        const int ntask = it.rows * ncg_valid;
+        for (int task = warp * tpw + sub; task < ntask; task += WG_PROD * tpw) {
+          if (sub >= tpw) continue;
+          const int jj = task / ncg_valid, cg = task - jj * ncg_valid;
+          const int e0 = (cg * 4 * oplane + (it.r0 + jj) * p.OW + it.c0 + 4 * gi) >> 2;
+          const int pl4 = oplane >> 2;
+          float4 v0 = __ldg(simg + e0), v1 = __ldg(simg + e0 + pl4), v2 = __ldg(simg + e0 + 2 * pl4),
+                 v3 = __ldg(simg + e0 + 3 * pl4);
+          if (mimg) {
+            const float4 m0 = __ldg(mimg + e0), m1 = __ldg(mimg + e0 + pl4), m2 = __ldg(mimg + e0 + 2 * pl4),
+                         m3 = __ldg(mimg + e0 + 3 * pl4);
+            v0.x = m0.x > 0.f ? v0.x : 0.f; v0.y = m0.y > 0.f ? v0.y : 0.f; v0.z = m0.z > 0.f ? v0.z : 0.f; v0.w = m0.w > 0.f ? v0.w : 0.f;
+            v1.x = m1.x > 0.f ? v1.x : 0.f; v1.y = m1.y > 0.f ? v1.y : 0.f; v1.z = m1.z > 0.f ? v1.z : 0.f; v1.w = m1.w > 0.f ? v1.w : 0.f;
+            v2.x = m2.x > 0.f ? v2.x : 0.f; v2.y = m2.y > 0.f ? v2.y : 0.f; v2.z = m2.z > 0.f ? v2.z : 0.f; v2.w = m2.w > 0.f ? v2.w : 0.f;
+            v3.x = m3.x > 0.f ? v3.x : 0.f; v3.y = m3.y > 0.f ? v3.y : 0.f; v3.z = m3.z > 0.f ? v3.z : 0.f; v3.w = m3.w > 0.f ? v3.w : 0.f;
+          }
+          const float px[4][4] = {{v0.x, v1.x, v2.x, v3.x}, {v0.y, v1.y, v2.y, v3.y},
+                                  {v0.z, v1.z, v2.z, v3.z}, {v0.w, v1.w, v2.w, v3.w}};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t off = (uint32_t)(jj * p.PWo + 4 * gi + j) * WG_ROWB;
+            wg_store_split(buf + off + wg_swz(buf_a + off, cg), p.o_half, px[j][0], px[j][1], px[j][2], px[j][3]);
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&band_full[ring.s]);
+    }
+  } else if (warp >= WG_MMA && warp < WG_MMA + WG_NISS) {
+    // ---------------- MMA issuers (chunks dealt round-robin) ----------------
+    const uint32_t me = (uint32_t)(warp - WG_MMA);
+    const uint32_t idesc = make_idesc_mn(p.mrows, WG_N);
+    // descriptor low word: start address >> 4 | LBO >> 4 << 16; high word: SBO = 512 B (4 rows),
+    // version 1, base offset 0, layout SWIZZLE_128B_BASE32B (= 1)
+    const uint32_t a_w0 = ((smem_u32(xb) & 0x3FFFFu) >> 4) | (((uint32_t)p.a_lbo >> 4) << 16);
+    const uint32_t b_w0 = ((smem_u32(ob) & 0x3FFFFu) >> 4) | ((512u >> 4) << 16);
+    const uint32_t hi_const = (512u >> 4) | (1u << 14) | (1u << 29);
+    const uint32_t xbuf16 = (uint32_t)p.x_buf >> 4, xhalf16 = (uint32_t)p.x_half >> 4;
+    const uint32_t obuf16 = (uint32_t)p.o_buf >> 4, ohalf16 = (uint32_t)p.o_half >> 4;
+    const uint32_t xrow16 = (uint32_t)(p.S * p.ncx * p.PWx) * (WG_ROWB >> 4);   // 16-byte units per output row of X
+    const uint32_t orow16 = (uint32_t)p.PWo * (WG_ROWB >> 4);
+    const int ksteps = p.PWo >> 3;
+    StageRing ring(2);
+    uint32_t ccount = 0, slot = 0, sphase = 0;
+    for (int item = first_item; item < nitems; item += item_step, ring.next()) {
+      const WgItem it = item_of(item);
+      mbar_wait(&band_full[ring.s], ring.par);
+      tc_fence_after();
+      const uint32_t a_buf = a_w0 + ring.s * xbuf16, b_buf = b_w0 + ring.s * obuf16;
+      for (int j0 = 0; j0 < it.rows; j0 += p.rpc, ++ccount) {
+        const uint32_t ab = slot, aphase = sphase;
+        if (++slot == WG_NSLOT) { slot = 0; sphase ^= 1u; }
+        if ((ccount & (WG_NISS - 1)) != me) continue;
+        mbar_wait(&acc_empty[ab], aphase ^ 1u);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t tmem_d = tmem_base + ab * WG_NACC;
+          const int j1 = min(it.rows, j0 + p.rpc);
+          uint32_t acc = 0;
+          for (int jj = j0; jj < j1; ++jj) {
+            uint32_t a_row = a_buf + (uint32_t)jj * xrow16;
+            uint32_t b_row = b_buf + (uint32_t)jj * orow16;
+            for (int kk = 0; kk < ksteps; ++kk) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                // stride 1: row x0 + kx; stride 2: parity plane kx & 1, row x0 + (kx >> 1)
+                const uint32_t a_hi = a_row + (p.ncx == 1 ? (uint32_t)kx : (uint32_t)((kx & 1) * p.PWx + (kx >> 1))) * 8u;
+                // (measured: the swizzle phase comes from the absolute address bits, so a start that is
+                //  not aligned to the 512-byte pattern needs NO base offset in the descriptor)
+                mma_tf32_w(tmem_d + kx * WG_N, a_hi + xhalf16, hi_const, b_row, hi_const, idesc, acc);
+                mma_tf32_w(tmem_d + kx * WG_N, a_hi, hi_const, b_row + ohalf16, hi_const, idesc, 1u);
+                mma_tf32_w(tmem_d + kx * WG_N, a_hi, hi_const, b_row, hi_const, idesc, 1u);
+              }
+              acc = 1u;
+              a_row += 8 * 8;
+              b_row += 8 * 8;
+            }
+          }
+        }
+        __syncwarp();
+        if (elect_one()) mma_commit(&acc_full[ab]);
+      }
+      if (elect_one()) mma_commit(&band_empty[ring.s]);
+    }
+  } else if (warp >= WG_DRAIN0 && warp < WG_DRAIN0 + NUM_EPI_WARPS) {
+    // ---------------- drain: running sums in registers ----------------
+    const int e = warp - WG_DRAIN0, q = e & 3, hsel = e >> 2;
+    float acc[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) acc[j] = 0.0f;
+    uint32_t slot = 0, sphase = 0;
+    for (int item = first_item; item < nitems; item += item_step) {
+      const WgItem it = item_of(item);
+      for (int j0 = 0; j0 < it.rows; j0 += p.rpc) {
+        const uint32_t ab = slot;
+        mbar_wait(&acc_full[ab], sphase);
+        if (++slot == WG_NSLOT) { slot = 0; sphase ^= 1u; }
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * WG_NACC + hsel * NC;
+#pragma unroll
+        for (int c0 = 0; c0 < NC; c0 += 16) {
+          uint32_t r[16];
+          wg_tmem_ld16(taddr + (uint32_t)c0, r);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      }
+    }
+    float* dst = p.partial + ((size_t)blockIdx.x * 128 + q * 32 + lane) * WG_NACC + hsel * NC;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) dst[j] = acc[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WG_ALLOC) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+  }
+}
+
+// dW from the per-CTA partials (double accumulation).  Accumulator row of (ky, ci):
+//   packed (stride 1, Cin <= 16) : ky * 16 + ci            otherwise : ky * 32 + ci
+// M = 64 accumulators live in TMEM lanes (m % 16) + 32 * (m / 16).
+__global__ void __launch_bounds__(256)
+wg_shift_reduce_kernel(const float* __restrict__ partial, int grid, int pack2, int mrows, int Cin, int Cout,
+                       int n0, float* __restrict__ dW) {
+  const int nco = min(WG_N, Cout - n0);
+  const int total = nco * Cin * 9;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int kx = e % 3;
+    int r = e / 3;
+    const int ky = r % 3;
+    r /= 3;
+    const int ci = r % Cin, co = r / Cin;
+    const int m = pack2 ? ky * 16 + ci : ky * 32 + ci;
+    const int lane_row = mrows == 128 ? m : (m & 15) + 32 * (m >> 4);
+    double s = 0.0;
+    for (int b = 0; b < grid; ++b)
+      s += (double)partial[((size_t)b * 128 + lane_row) * WG_NACC + kx * WG_N + co];
+    dW[(((size_t)(n0 + co) * Cin + ci) * 3 + ky) * 3 + kx] = (float)s;
+  }
+}
+
+// dbias[c] = sum over images and positions of dY (where Ymask > 0)
+__global__ void __launch_bounds__(256)
+wg_bias_sum_kernel(const float* __restrict__ dY, const float* __restrict__ mask, double* __restrict__ acc, int N,
+                   int C, int HW4) {
+  __shared__ double scratch[32];
+  const int c = blockIdx.y;
+  double s = 0.0;
+  const long long per = (long long)N * HW4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW4);
+    const long long a = ((long long)n * C + c) * HW4 + (i - (long long)n * HW4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(dY) + a);
+    float t;
+    if (mask) {
+      const float4 m = __ldg(reinterpret_cast<const float4*>(mask) + a);
+      t = ((m.x > 0.f ? v.x : 0.f) + (m.y > 0.f ? v.y : 0.f)) + ((m.z > 0.f ? v.z : 0.f) + (m.w > 0.f ? v.w : 0.f));
+    } else {
+      t = (v.x + v.y) + (v.z + v.w);
+    }
+    s += (double)t;
+  }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) atomicAdd(&acc[c], s);
+}
+__global__ void wg_bias_finish_kernel(const double* __restrict__ acc, float* __restrict__ out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) out[c] = (float)acc[c];
+}
+
+static constexpr int WG_SMEM_LIMIT = 227 * 1024;
+
+static size_t wg_smem_bytes(const WgShiftParams& p) {
+  return 2 * (size_t)p.x_buf + 2 * (size_t)p.o_buf + 8192 + 1024 + 256;
+}
+
+static bool wg_plan(WgShiftParams* p) {
+  for (int rb = p->OH; rb >= 1; --rb) {
+    const int nb = cdiv(p->OH, rb);
+    p->Rb = cdiv(p->OH, nb);
+    p->nbands = nb;
+    p->xrows = p->S == 1 ? p->Rb + 2 : 2 * p->Rb + 1;
+    // every hi / lo copy and buffer stays 1024-byte aligned (the swizzle phase is taken from address bits)
+    const long long xh = ((long long)p->xrows * p->ncx * p->PWx * WG_ROWB + 1023) & ~1023LL;
+    const long long oh = ((long long)p->Rb * p->PWo * WG_ROWB + 1023) & ~1023LL;
+    p->x_half = (int)xh; p->x_buf = (int)(2 * xh);
+    p->o_half = (int)oh; p->o_buf = (int)(2 * oh);
+    if (wg_smem_bytes(*p) <= (size_t)WG_SMEM_LIMIT) return true;
+  }
+  return false;
+}
+
+}  // namespace tc
+
+static bool wg_shift_enabled() {
+  static const bool off = getenv("A2C_NO_SHIFT") != nullptr || getenv("A2C_NO_SHIFT_WGRAD") != nullptr;
+  return !off;
+}
+
+long long conv_wgrad_shift_workspace(const a2c_conv_shape* s) {
+  return (long long)num_sms() * 128 * tc::WG_NACC * 4 + (long long)(s ? s->Cout + 2 : 2) * 8 + 256;
+}
+
+bool conv_wgrad_shift_ok(const a2c_conv_shape* s) {
+  const int S = s->stride;
+  if (!wg_shift_enabled() || s->K != 3 || s->pad != 1 || (S != 1 && S != 2)) return false;
+  if ((s->Cin & 3) || (s->Cout & 3) || s->Cin > 32 || (s->W & 3) || (s->OW & 3)) return false;
+  if (S == 2 && ((s->H | s->W) & 1)) return false;
+  const int ncol = cdiv(s->OW, S == 1 ? 40 : 20);
+  return s->OW % ncol == 0 && ((s->OW / ncol) & 3) == 0;
+}
+
+// 0 = ran, 1 = not supported (caller falls back), else error
+int conv_wgrad_shift_try(const float* X, const float* dY, const float* Ymask, float* dW, float* dbias, int N,
+                         const a2c_conv_shape* s, void* workspace, long long workspace_bytes, cudaStream_t st) {
+  const int K = s->K, S = s->stride, P = s->pad;
+  (void)K; (void)P;
+  if (!X || !conv_wgrad_shift_ok(s)) return 1;
+  if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(dY) & 15) ||
+      (Ymask && (reinterpret_cast<uintptr_t>(Ymask) & 15)))
+    return 1;
+  if (workspace_bytes < conv_wgrad_shift_workspace(s)) return 1;
+  static thread_local tc::WgShiftParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = X; p.dy = dY; p.mask = Ymask; p.N = N; p.Cin = s->Cin; p.H = s->H; p.W = s->W;
+  p.Cout = s->Cout; p.OH = s->OH; p.OW = s->OW; p.S = S; p.ncx = S;
+  // column chunks of at most 40 (stride 2: 20) output positions (multiple of 4) that tile the row exactly
+  p.ncol = cdiv(s->OW, S == 1 ? 40 : 20);
+  if (s->OW % p.ncol) return 1;
+  p.OWc = s->OW / p.ncol;
+  if (p.OWc & 3) return 1;
+  p.PWx = S == 1 ? p.OWc + 2 : p.OWc + 1;
+  p.PWo = (p.OWc + 7) & ~7;
+  p.pack2 = (S == 1 && s->Cin <= 16) ? 1 : 0;
+  p.mrows = p.pack2 ? 64 : 128;
+  p.a_lbo = (p.pack2 ? 2 : 1) * p.ncx * p.PWx * tc::WG_ROWB;     // one (packed: two) source rows
+  if (p.a_lbo >= (1 << 18)) return 1;
+  if (!tc::wg_plan(&p)) return 1;
+  // rows per accumulator chunk: a TMEM chain of at most ~64 MMAs (3 per k-step)
+  const int ksteps = p.PWo / 8;
+  p.rpc = 20 / ksteps;
+  if (p.rpc < 1) p.rpc = 1;
+  double* bias_acc = reinterpret_cast<double*>(workspace);
+  p.partial = reinterpret_cast<float*>(bias_acc + ((s->Cout + 1) & ~1));
+  { const char* e = getenv("A2C_WG_DBG"); p.dbg = e ? atoi(e) : 0; }
+  auto kern = tc::conv_shift_wgrad_kernel;
+  static bool configured = false;
+  if (!configured) {
+    A2C_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WG_SMEM_LIMIT));
+    configured = true;
+  }
+  int grid = num_sms();
+  const int items = N * p.nbands * p.ncol;
+  if (grid > items) grid = items;
+  for (int n0 = 0; n0 < s->Cout; n0 += tc::WG_N) {
+    p.n0 = n0;
+    kern<<<grid, tc::WG_THREADS, tc::wg_smem_bytes(p), st>>>(p);
+    g_launches++;
+    A2C_LAUNCH_CHECK();
+    const int nco = s->Cout - n0 < tc::WG_N ? s->Cout - n0 : tc::WG_N;
+    tc::wg_shift_reduce_kernel<<<cdiv(nco * s->Cin * 9, 256), 256, 0, st>>>(p.partial, grid, p.pack2, p.mrows,
+                                                                            s->Cin, s->Cout, n0, dW);
+    g_launches++;
+    A2C_LAUNCH_CHECK();
+  }
+  if (dbias) {
+    A2C_CUDA_CHECK(cudaMemsetAsync(bias_acc, 0, sizeof(double) * s->Cout, st));
+    const int hw4 = s->OH * s->OW / 4;
+    int bx = (int)cdivll((long long)N * hw4, 256 * 4);
+    if (bx > 128) bx = 128;
+    if (bx < 1) bx = 1;
+    tc::wg_bias_sum_kernel<<<dim3(bx, s->Cout), 256, 0, st>>>(dY, Ymask, bias_acc, N, s->Cout, hw4);
+    tc::wg_bias_finish_kernel<<<cdiv(s->Cout, 64), 64, 0, st>>>(bias_acc, dbias, s->Cout);
+    g_launches += 2;
+    A2C_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace a2c
