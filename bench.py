@@ -238,6 +238,17 @@ def run_ours(args):
         step(True)
     ms_e2e, _, info_e2e, _ = timed(True, args.steps)
 
+    # stage 1 alone, launches back to back (inside a step it is followed by a host sync, so its
+    # per-call event time there includes the launch gap): 516 MB of frames per launch > L2
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(20):
+        ring.push_frames(d_new_frames, d_new_reset, first_frame_index=1)
+    s1.record()
+    barrier()
+    stage1_ms = s0.elapsed_time(s1) / 20
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -246,20 +257,22 @@ def run_ours(args):
     value = total_tr / (ms / 1e3)
     e2e_value = total_tr / (ms_e2e / 1e3)
     pk = peaks()
-    roof, table = roofline_from_profile(prof, args.steps, R, T, pk)
+    roof, table = roofline_from_profile(prof, args.steps, R, T, pk, stage1_ms, args.precision)
     h2d = (R * T * 38400 + h_reset.numel()
            + sum(h_in[k].numel() * h_in[k].element_size() for k in h_in))
     out = {
         "metric": METRIC, "value": value, "unit": "transitions/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {0: "f32 (FFMA)", 1: "f32 (GEMMs: 3xTF32 split on tcgen05, fp32 accumulate; convs: FFMA)",
-                  2: "tf32 (single pass)"}[args.precision],
+        "dtype": "tf32" if args.precision == 2 else "f32",
         "data": "synthetic",
         "config": {"workload": desc, "model": model, "n_envs_per_gpu": R, "n_tsteps": T,
                    "transitions_per_step": N * world, "parallelism": "env-sharded dp%d" % world,
                    "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (R * T * FRAME_BYTES / 1e6),
-                   "optim": hyps["optim_type"]},
+                   "optim": hyps["optim_type"],
+                   "arithmetic": {0: "fp32 FFMA kernels", 1: "fp32 results via the 3xTF32 split on tcgen05 "
+                                  "(fp32 accumulate, 1e-5 parity); first conv layer on fp32 FFMA",
+                                  2: "single-pass TF32 on tcgen05 (2e-3)"}[args.precision]},
         "e2e": {"value": e2e_value, "unit": "transitions/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 20,
                 "h2d_note": "frames are read zero-copy by the stage-1 TMA kernel from pinned host "
@@ -276,7 +289,13 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def roofline_from_profile(prof, steps, R, T, pk):
+def ncu_traffic():
+    """DRAM bytes per launch from the committed `ncu --set full` captures (profiles/*.json)."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    return json.load(open(path)) if os.path.isfile(path) else {}
+
+
+def roofline_from_profile(prof, steps, R, T, pk, stage1_ms, precision):
     """prof: {key: [(start_evt, end_evt, work), ...]} recorded around each C-ABI
     call in the timed region (events on the launching stream).  Picks the entry
     with the largest total time as the dominant kernel."""
@@ -290,28 +309,32 @@ def roofline_from_profile(prof, steps, R, T, pk):
     rows.sort(reverse=True)
     total_ms = sum(r[0] for r in rows)
     table = [{"call": k, "launches": n, "ms_per_step": t / steps, "share": t / total_ms}
-             for t, k, n, _ in rows[:12]]
+             for t, k, n, _ in rows[:14]]
     t, key, n, work = rows[0]
     kind = key.split("|")[1] if "|" in key else "flops"
     per_launch_ms = t / n
+    traffic = ncu_traffic()
     if kind == "bytes":
         ach = work / n / (per_launch_ms / 1e3) / 1e9
         roof = {"kernel": key, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": ach / pk["hbm_gbs"], "traffic": None}
+                "frac": ach / pk["hbm_gbs"], "traffic": traffic.get(key)}
     else:
         ach = work / n / (per_launch_ms / 1e3) / 1e12
         roof = {"kernel": key, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"],
-                "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None,
-                "note": "peak = measured sustained cuBLAS bf16; fp32 FFMA peak of the part is ~72 TFLOP/s"}
+                "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic.get(key),
+                "note": "achieved = algorithmic fp32 flops (2*M*N*K) / launch time; peak = measured "
+                        "sustained cuBLAS bf16.  The fp32-parity path issues 3 TF32 MMAs per product "
+                        "(TF32 rate = bf16 / 2), so the tensor pipe itself runs at 6x this fraction"}
+        if precision == 1:
+            roof["frac_of_tf32_issued"] = 6.0 * ach / pk["bf16_tflops"]
     roof["launch_ms"] = per_launch_ms
     roof["peak_source"] = pk["src"]
-    # stage 1 is always reported as well (the memory-bound stage of the north star)
-    for tt, k, nn, w in rows:
-        if k.startswith("a2c_obs_prep_stack"):
-            a = w / nn / (tt / nn / 1e3) / 1e9
-            roof["stage1_hbm"] = {"achieved": a, "peak": pk["hbm_gbs"], "frac": a / pk["hbm_gbs"],
-                                  "frac_of_8TBps": a / 8000.0, "unit": "GB/s",
-                                  "launch_ms": tt / nn}
+    # stage 1 (the memory-bound stage of the north star) is always reported, timed alone
+    a = R * T * ALG_BYTES_PREP / (stage1_ms / 1e3) / 1e9
+    roof["stage1_hbm"] = {"kernel": "a2c_obs_prep_stack", "achieved": a, "peak": pk["hbm_gbs"],
+                          "frac": a / pk["hbm_gbs"], "unit": "GB/s", "launch_ms": stage1_ms,
+                          "bytes_per_transition": ALG_BYTES_PREP,
+                          "traffic": traffic.get("a2c_obs_prep_stack")}
     return roof, table
 
 

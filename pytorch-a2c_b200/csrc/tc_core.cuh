@@ -27,6 +27,7 @@ namespace tc {
 constexpr int TM = 128;            // UMMA M (cta_group::1)
 constexpr int KB = 32;             // k-block: 32 fp32 = one 128-byte swizzle row
 constexpr int NUM_EPI_WARPS = 8;
+constexpr int TILE_GROUP_M = 8;     // m-tiles per band of the grouped tile order
 constexpr int SCRATCH_BYTES = 4096;  // per-CTA scratch handed to Problem::init
 constexpr int MAX_THREADS = 704;     // 8 A + 4 B producer warps + 8 drain + MMA + allocator
 
@@ -165,7 +166,7 @@ __device__ __forceinline__ void store_elem(uint8_t* hi_tile, uint8_t* lo_tile, i
 // t = thread index within the operand's producer warps.
 template <int BN, bool SPLIT3, class P>
 __global__ void __launch_bounds__(32 * (P::NA + P::NB + NUM_EPI_WARPS + 2), 1)
-tc_kernel(const typename P::Params p, int stages, int mtiles) {
+tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
   constexpr int NUM_PROD_WARPS = P::NA + P::NB;
   constexpr int KC = P::KC;
   constexpr int EPI0 = NUM_PROD_WARPS, MMA_WARP = EPI0 + NUM_EPI_WARPS, ALLOC_WARP = MMA_WARP + 1;
@@ -187,8 +188,20 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
 
   // shuffle-broadcast marks the warp index as warp-uniform for the compiler (uniform role branches)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  // persistent over m tiles: this CTA owns tiles blockIdx.y, blockIdx.y + gridDim.y, ...
+  // Persistent CTAs walk the output tiles in GROUPED order: tile t -> a band of TILE_GROUP_M m-tiles
+  // swept along n.  The ~148 tiles in flight then form a compact 2-D block, so A and B tiles are
+  // shared through L2 (with one n-tile per CTA and a loop over m, the B tiles of 148 CTAs did not
+  // fit in L2 and the dgrad / wgrad GEMMs re-read 8-11x their operands from HBM).
+  const int total_tiles = mtiles * ntiles;
+  const int tile0 = blockIdx.x, tile_step = gridDim.x;
+  auto tile_of = [&](int t, int& mt, int& nt) {
+    const int per_group = TILE_GROUP_M * ntiles;
+    const int g = t / per_group, r = t - g * per_group;
+    const int first_m = g * TILE_GROUP_M;
+    const int gsize = min(TILE_GROUP_M, mtiles - first_m);
+    nt = r / gsize;
+    mt = first_m + (r - nt * gsize);
+  };
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int kb_end = min(p.nkb, kb_begin + p.kb_per_split);
   const int nkb = kb_end - kb_begin;
@@ -223,19 +236,24 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
     // ---- A producers: the global loads of k-block i+1 are issued before k-block i is
     // converted and stored, so their latency overlaps the stage hand-shake and the stores
     const int t = threadIdx.x;
-    int mt = blockIdx.y, i = 0, it = 0;
+    int tile = tile0, i = 0, it = 0;
     StageRing ring(stages);
-    if (mt < mtiles && nkb > 0) {
+    if (tile < total_tiles && nkb > 0) {
       typename P::AState ast;
       typename P::AFrag cur, nxt;
+      int mt, nt;
+      tile_of(tile, mt, nt);
       P::a_setup(p, scratch, mt * TM, t, ast);
       P::load_a(p, ast, scratch, mt * TM, kb_begin, t, cur);
       while (true) {
-        int ni = i + 1, nmt = mt;
-        if (ni == nkb) { ni = 0; nmt = mt + gridDim.y; }
-        const bool has_next = nmt < mtiles;
+        int ni = i + 1, ntile = tile, nmt = mt;
+        if (ni == nkb) { ni = 0; ntile = tile + tile_step; }
+        const bool has_next = ntile < total_tiles;
         if (has_next) {
-          if (nmt != mt) P::a_setup(p, scratch, nmt * TM, t, ast);
+          if (ntile != tile) {
+            tile_of(ntile, nmt, nt);
+            if (nmt != mt) P::a_setup(p, scratch, nmt * TM, t, ast);
+          }
           P::load_a(p, ast, scratch, nmt * TM, kb_begin + ni, t, nxt);
         }
         const int s = ring.s;
@@ -246,22 +264,27 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
         if (!has_next) break;
-        cur = nxt; mt = nmt; i = ni; ++it; ring.next();
+        cur = nxt; mt = nmt; tile = ntile; i = ni; ++it; ring.next();
       }
     }
   } else if (warp < NUM_PROD_WARPS) {
     // ---- B producers (same pipelining; the B tile depends on the k-block only)
     const int t = (int)threadIdx.x - 32 * P::NA;
-    int mt = blockIdx.y, i = 0, it = 0;
+    int tile = tile0, i = 0, it = 0;
     StageRing ring(stages);
-    if (mt < mtiles && nkb > 0) {
+    if (tile < total_tiles && nkb > 0) {
       typename P::BFrag cur, nxt;
-      P::load_b(p, scratch, n0, kb_begin, t, cur);
+      int mt, nt;
+      tile_of(tile, mt, nt);
+      P::load_b(p, scratch, nt * BN, kb_begin, t, cur);
       while (true) {
-        int ni = i + 1, nmt = mt;
-        if (ni == nkb) { ni = 0; nmt = mt + gridDim.y; }
-        const bool has_next = nmt < mtiles;
-        if (has_next) P::load_b(p, scratch, n0, kb_begin + ni, t, nxt);
+        int ni = i + 1, ntile = tile;
+        if (ni == nkb) { ni = 0; ntile = tile + tile_step; }
+        const bool has_next = ntile < total_tiles;
+        if (has_next) {
+          if (ntile != tile) tile_of(ntile, mt, nt);
+          P::load_b(p, scratch, nt * BN, kb_begin + ni, t, nxt);
+        }
         const int s = ring.s;
         mbar_wait(&empty[s], ring.par ^ 1);
         uint8_t* b = stage_ptr(s) + (SPLIT3 ? 2 : 1) * A_BYTES;
@@ -270,14 +293,14 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
         if (!has_next) break;
-        cur = nxt; mt = nmt; i = ni; ++it; ring.next();
+        cur = nxt; tile = ntile; i = ni; ++it; ring.next();
       }
     }
   } else if (warp == MMA_WARP) {
     constexpr uint32_t idesc = make_idesc(BN);
     int it = 0, gchunk0 = 0;
     StageRing ring(stages);
-    for (int mt = blockIdx.y; mt < mtiles; mt += gridDim.y, gchunk0 += nchunks)
+    for (int tile = tile0; tile < total_tiles; tile += tile_step, gchunk0 += nchunks)
     for (int i = 0; i < nkb; ++i, ++it, ring.next()) {
       const int s = ring.s;
       const uint32_t parity = ring.par;
@@ -319,8 +342,10 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
     // ---- drain + epilogue: thread <-> accumulator row (TMEM lane), half of the columns ----
     const int e = warp - EPI0, q = e & 3, hsel = e >> 2;
     int gchunk = 0;
-    for (int mt = blockIdx.y; mt < mtiles; mt += gridDim.y) {
-    const int m0 = mt * TM;
+    for (int tile = tile0; tile < total_tiles; tile += tile_step) {
+    int mt, nt;
+    tile_of(tile, mt, nt);
+    const int m0 = mt * TM, n0 = nt * BN;
     float acc[HALF];
 #pragma unroll
     for (int j = 0; j < HALF; ++j) acc[j] = 0.0f;
@@ -362,7 +387,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles) {
 template <int BN, bool SPLIT3>
 constexpr int stage_bytes() { return (SPLIT3 ? 2 : 1) * (TM * 128 + BN * 128); }
 
-// Launch helper: grid = (n tiles, m tiles, splits).
+// Launch helper: grid = (persistent CTAs, 1, splits).
 template <int BN, bool SPLIT3, class P>
 int tc_launch(const typename P::Params& p, int mtiles, int ntiles, int splits, cudaStream_t st) {
   constexpr int SB = stage_bytes<BN, SPLIT3>();
@@ -380,12 +405,12 @@ int tc_launch(const typename P::Params& p, int mtiles, int ntiles, int splits, c
     }
     configured = true;
   }
-  // one CTA per SM (the tile ring takes most of shared memory): persistent over m tiles
-  int gy = mtiles;
-  const int cap = num_sms() / (ntiles * splits > 0 ? ntiles * splits : 1);
-  if (gy > cap) gy = cap < 1 ? 1 : cap;
-  dim3 grid(ntiles, gy, splits);
-  kern<<<grid, 32 * (P::NA + P::NB + NUM_EPI_WARPS + 2), smem, st>>>(p, stages, mtiles);
+  // one CTA per SM (the tile ring takes most of shared memory): persistent over the output tiles
+  int ncta = num_sms() / (splits > 0 ? splits : 1);
+  if (ncta < 1) ncta = 1;
+  if (ncta > mtiles * ntiles) ncta = mtiles * ntiles;
+  dim3 grid(ncta, 1, splits);
+  kern<<<grid, 32 * (P::NA + P::NB + NUM_EPI_WARPS + 2), smem, st>>>(p, stages, mtiles, ntiles);
   return 0;
 }
 
