@@ -12,6 +12,9 @@
 //   stride 1, Cin <= 16 : every X row also carries the channels of the image row below it in
 //                         slots [16, 32), so one 32-slot atom covers ky = 0, 1 and a second atom
 //                         two image rows further down covers ky = 2: M = 64, one MMA per kx.
+//   stride 1, Cin <= 4  : (first layers) rows y, y+1, y+2 share one atom, 4 slots each: M = 64.
+//                         The input may be the uint8 plane ring (state view): {0,1} values are
+//                         exact in TF32, so the x_lo * dy_hi product is skipped.
 //   stride 1, Cin  > 16 : atoms of rows y, y+1, y+2 stack along M (M = 128).
 //   stride 2            : source rows are stored one after the other, each split into its two
 //                         x-parity planes; the atoms of rows 2oy-1, 2oy, 2oy+1 stack along M.
@@ -45,7 +48,11 @@ constexpr int WG_ROWB = 128;                 // bytes of one position row (32 sl
 static_assert(WG_DRAIN0 % 4 == 0, "drain warps must start at a multiple of 4");
 
 struct WgShiftParams {
-  const float* x;        // f32 [N][Cin][H][W]
+  const float* x;        // f32 [N][Cin][H][W] (NULL when use_view)
+  a2c_state_view view;   // first-layer source: uint8 plane ring
+  int use_view;
+  int pack3;             // Cin <= 4: slots [4ky, 4ky+4) of a row = channels of image row y + ky
+  int nsplit;            // 2: X has a lo part (3 MMAs per product), 1: X exact in TF32 (2 MMAs)
   const float* dy;       // f32 [N][Cout][OH][OW]
   const float* mask;     // optional (layer output Y): dY counts only where mask > 0
   int N, Cin, H, W, Cout, OH, OW;
@@ -159,8 +166,69 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
     for (int item = first_item; item < nitems; item += item_step, ring.next()) {
       const WgItem it = item_of(item);
       mbar_wait_relaxed(&band_empty[ring.s], ring.par ^ 1);
+      if (p.pack3) {
+        // --- first layer: <= 4 channels, f32 tensor or uint8 ring view; a row's pixel goes to
+        //     chunk ky of row r - ky (ky = 0, 1, 2) ---
+        uint8_t* buf = xb + (size_t)ring.s * p.x_buf;
+        const uint32_t buf_a = smem_u32(buf);
+        const int xs = it.c0 - 1, xe = it.c0 + p.OWc + 1;
+        const int g0 = (xs < 0 ? xs - 3 : xs) / 4;
+        const int ng = (xe + 3) / 4 - g0;
+        const int tpw = 32 / ng > 0 ? 32 / ng : 1;
+        const int sub = lane / ng, gi = lane - sub * ng;
+        long long ibase = (long long)it.img * p.Cin * xplane, cstride = xplane;
+        uint32_t cmask = 0xfu;
+        if (p.use_view) {
+          const long long rr = it.img / p.view.T;
+          const int tt = it.img - (int)rr * p.view.T;
+          ibase = rr * p.view.stride_r + (long long)tt * p.view.stride_t;
+          cstride = p.view.stride_c;
+          if (p.view.pflag) {                       // planes older than a reset read as zero (a2c/utils.py:37-40)
+            const uint8_t* pf = p.view.pflag + rr * p.view.pflag_stride_r + tt;
+            cmask = 0;
+            bool live = true;
+            for (int c = p.view.fs - 1; c >= 0; --c) {
+              if (live) cmask |= 1u << c;
+              live = live && (pf[c] == 0);
+            }
+          }
+        }
+        const int nrow = it.rows + 2;
+        for (int r = warp * tpw + sub; r < nrow; r += WG_PROD * tpw) {
+          if (sub >= tpw) continue;
+          const int sy = it.r0 + r - 1;
+          const int x4 = 4 * (g0 + gi);
+          const bool ok = (unsigned)sy < (unsigned)p.H && (unsigned)x4 < (unsigned)p.W;
+          float px[4][4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && c < p.Cin && ((cmask >> c) & 1u)) {
+              const long long a = ibase + c * cstride + (long long)sy * p.W + x4;
+              if (p.use_view) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.view.base) + a));
+                v = make_float4((float)(w & 0xff), (float)((w >> 8) & 0xff), (float)((w >> 16) & 0xff), (float)(w >> 24));
+              } else {
+                v = __ldg(reinterpret_cast<const float4*>(p.x + a));
+              }
+            }
+            px[0][c] = v.x; px[1][c] = v.y; px[2][c] = v.z; px[3][c] = v.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int xp = x4 + j - xs;
+            if (xp < 0 || x4 + j >= xe) continue;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              if (r - k < 0) continue;
+              const uint32_t off = (uint32_t)((r - k) * p.PWx + xp) * WG_ROWB;
+              wg_store_split(buf + off + wg_swz(buf_a + off, k), p.x_half, px[j][0], px[j][1], px[j][2], px[j][3]);
+            }
+          }
+        }
+      } else {
       // --- X band.  A lane converts 4 consecutive pixels (one float4 per channel) of 4 channels. ---
-      {
+
         uint8_t* buf = xb + (size_t)ring.s * p.x_buf;
         const uint32_t buf_a = smem_u32(buf);
         const float4* simg = reinterpret_cast<const float4*>(p.x + (long long)it.img * p.Cin * xplane);
@@ -283,8 +351,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
                 const uint32_t a_hi = a_row + (p.ncx == 1 ? (uint32_t)kx : (uint32_t)((kx & 1) * p.PWx + (kx >> 1))) * 8u;
                 // (measured: the swizzle phase comes from the absolute address bits, so a start that is
                 //  not aligned to the 512-byte pattern needs NO base offset in the descriptor)
-                mma_tf32_w(tmem_d + kx * WG_N, a_hi + xhalf16, hi_const, b_row, hi_const, idesc, acc);
-                mma_tf32_w(tmem_d + kx * WG_N, a_hi, hi_const, b_row + ohalf16, hi_const, idesc, 1u);
+                if (p.nsplit == 2) {
+                  mma_tf32_w(tmem_d + kx * WG_N, a_hi + xhalf16, hi_const, b_row, hi_const, idesc, acc);
+                  mma_tf32_w(tmem_d + kx * WG_N, a_hi, hi_const, b_row + ohalf16, hi_const, idesc, 1u);
+                } else {
+                  mma_tf32_w(tmem_d + kx * WG_N, a_hi, hi_const, b_row + ohalf16, hi_const, idesc, acc);
+                }
                 mma_tf32_w(tmem_d + kx * WG_N, a_hi, hi_const, b_row, hi_const, idesc, 1u);
               }
               acc = 1u;
@@ -339,10 +411,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
 }
 
 // dW from the per-CTA partials (double accumulation).  Accumulator row of (ky, ci):
-//   packed (stride 1, Cin <= 16) : ky * 16 + ci            otherwise : ky * 32 + ci
+//   first layer (Cin <= 4) : ky * 4 + ci     packed (stride 1, Cin <= 16) : ky * 16 + ci     otherwise : ky * 32 + ci
 // M = 64 accumulators live in TMEM lanes (m % 16) + 32 * (m / 16).
 __global__ void __launch_bounds__(256)
-wg_shift_reduce_kernel(const float* __restrict__ partial, int grid, int pack2, int mrows, int Cin, int Cout,
+wg_shift_reduce_kernel(const float* __restrict__ partial, int grid, int pack, int mrows, int Cin, int Cout,
                        int n0, float* __restrict__ dW) {
   const int nco = min(WG_N, Cout - n0);
   const int total = nco * Cin * 9;
@@ -352,7 +424,7 @@ wg_shift_reduce_kernel(const float* __restrict__ partial, int grid, int pack2, i
     const int ky = r % 3;
     r /= 3;
     const int ci = r % Cin, co = r / Cin;
-    const int m = pack2 ? ky * 16 + ci : ky * 32 + ci;
+    const int m = pack == 3 ? ky * 4 + ci : (pack == 2 ? ky * 16 + ci : ky * 32 + ci);
     const int lane_row = mrows == 128 ? m : (m & 15) + 32 * (m >> 4);
     double s = 0.0;
     for (int b = 0; b < grid; ++b)
@@ -426,25 +498,36 @@ long long conv_wgrad_shift_workspace(const a2c_conv_shape* s) {
 bool conv_wgrad_shift_ok(const a2c_conv_shape* s) {
   const int S = s->stride;
   if (!wg_shift_enabled() || s->K != 3 || s->pad != 1 || (S != 1 && S != 2)) return false;
-  if ((s->Cin & 3) || (s->Cout & 3) || s->Cin > 32 || (s->W & 3) || (s->OW & 3)) return false;
+  const bool first = s->Cin <= 4 && S == 1;
+  if ((!first && (s->Cin & 3)) || (s->Cout & 3) || s->Cin > 32 || (s->W & 3) || (s->OW & 3)) return false;
   if (S == 2 && ((s->H | s->W) & 1)) return false;
   const int ncol = cdiv(s->OW, S == 1 ? 40 : 20);
   return s->OW % ncol == 0 && ((s->OW / ncol) & 3) == 0;
 }
 
 // 0 = ran, 1 = not supported (caller falls back), else error
-int conv_wgrad_shift_try(const float* X, const float* dY, const float* Ymask, float* dW, float* dbias, int N,
-                         const a2c_conv_shape* s, void* workspace, long long workspace_bytes, cudaStream_t st) {
-  const int K = s->K, S = s->stride, P = s->pad;
-  (void)K; (void)P;
-  if (!X || !conv_wgrad_shift_ok(s)) return 1;
-  if ((reinterpret_cast<uintptr_t>(X) & 15) || (reinterpret_cast<uintptr_t>(dY) & 15) ||
+int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const float* dY, const float* Ymask,
+                         float* dW, float* dbias, int N, const a2c_conv_shape* s, void* workspace,
+                         long long workspace_bytes, cudaStream_t st) {
+  const int S = s->stride;
+  if ((!X && !xview) || !conv_wgrad_shift_ok(s)) return 1;
+  const bool first = s->Cin <= 4 && S == 1;
+  if (xview) {
+    // uint8 plane ring only: 4-byte aligned rows, one plane per channel
+    if (!first || xview->dtype != 0 || xview->fs != s->Cin || (reinterpret_cast<uintptr_t>(xview->base) & 3) ||
+        ((xview->stride_r | xview->stride_t | xview->stride_c) & 3))
+      return 1;
+  }
+  if ((X && (reinterpret_cast<uintptr_t>(X) & 15)) || (reinterpret_cast<uintptr_t>(dY) & 15) ||
       (Ymask && (reinterpret_cast<uintptr_t>(Ymask) & 15)))
     return 1;
   if (workspace_bytes < conv_wgrad_shift_workspace(s)) return 1;
   static thread_local tc::WgShiftParams p;
   memset(&p, 0, sizeof(p));
-  p.x = X; p.dy = dY; p.mask = Ymask; p.N = N; p.Cin = s->Cin; p.H = s->H; p.W = s->W;
+  p.x = xview ? nullptr : X; p.dy = dY; p.mask = Ymask; p.N = N; p.Cin = s->Cin; p.H = s->H; p.W = s->W;
+  if (xview) { p.view = *xview; p.use_view = 1; }
+  p.pack3 = first ? 1 : 0;
+  p.nsplit = xview ? 1 : 2;
   p.Cout = s->Cout; p.OH = s->OH; p.OW = s->OW; p.S = S; p.ncx = S;
   // column chunks of at most 40 (stride 2: 20) output positions (multiple of 4) that tile the row exactly
   p.ncol = cdiv(s->OW, S == 1 ? 40 : 20);
@@ -453,8 +536,8 @@ int conv_wgrad_shift_try(const float* X, const float* dY, const float* Ymask, fl
   if (p.OWc & 3) return 1;
   p.PWx = S == 1 ? p.OWc + 2 : p.OWc + 1;
   p.PWo = (p.OWc + 7) & ~7;
-  p.pack2 = (S == 1 && s->Cin <= 16) ? 1 : 0;
-  p.mrows = p.pack2 ? 64 : 128;
+  p.pack2 = (S == 1 && s->Cin <= 16 && !first) ? 1 : 0;
+  p.mrows = (p.pack2 || p.pack3) ? 64 : 128;
   p.a_lbo = (p.pack2 ? 2 : 1) * p.ncx * p.PWx * tc::WG_ROWB;     // one (packed: two) source rows
   if (p.a_lbo >= (1 << 18)) return 1;
   if (!tc::wg_plan(&p)) return 1;
@@ -480,7 +563,7 @@ int conv_wgrad_shift_try(const float* X, const float* dY, const float* Ymask, fl
     g_launches++;
     A2C_LAUNCH_CHECK();
     const int nco = s->Cout - n0 < tc::WG_N ? s->Cout - n0 : tc::WG_N;
-    tc::wg_shift_reduce_kernel<<<cdiv(nco * s->Cin * 9, 256), 256, 0, st>>>(p.partial, grid, p.pack2, p.mrows,
+    tc::wg_shift_reduce_kernel<<<cdiv(nco * s->Cin * 9, 256), 256, 0, st>>>(p.partial, grid, p.pack3 ? 3 : (p.pack2 ? 2 : 0), p.mrows,
                                                                             s->Cin, s->Cout, n0, dW);
     g_launches++;
     A2C_LAUNCH_CHECK();

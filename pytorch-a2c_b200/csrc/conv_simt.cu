@@ -475,8 +475,9 @@ int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, f
 bool conv_dgrad_shift_ok(const a2c_conv_shape* s);
 bool conv_wgrad_shift_ok(const a2c_conv_shape* s);
 long long conv_wgrad_shift_workspace(const a2c_conv_shape* s);
-int conv_wgrad_shift_try(const float* X, const float* dY, const float* Ymask, float* dW, float* dbias, int N,
-                         const a2c_conv_shape* s, void* workspace, long long workspace_bytes, cudaStream_t st);
+int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const float* dY, const float* Ymask,
+                         float* dW, float* dbias, int N, const a2c_conv_shape* s, void* workspace,
+                         long long workspace_bytes, cudaStream_t st);
 
 int conv_fwd_patch_try(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias,
                        float* Y, int N, const a2c_conv_shape* s, int relu, int precision, cudaStream_t st);
@@ -550,7 +551,7 @@ int a2c_conv2d_fused_mask(const a2c_conv_shape* s, int precision, int input_is_v
   if (precision == 0) return 3;                       // the FFMA kernels always take Ymask
   int bits = 0;
   if (precision == 1 && conv_dgrad_shift_ok(s)) bits |= 1;
-  if ((precision == 1 && !input_is_view && conv_wgrad_shift_ok(s)) || s->Cin <= 4) bits |= 2;
+  if ((precision == 1 && (!input_is_view || s->Cin <= 4) && conv_wgrad_shift_ok(s)) || s->Cin <= 4) bits |= 2;
   return bits;
 }
 
@@ -586,8 +587,8 @@ int a2c_conv2d_bwd_weight(const float* X, const a2c_state_view* xview, const flo
   // First layers (Cin <= 4, {0,1} inputs, gradients that are sums of ~1e7 cancelling terms) stay on
   // the FFMA kernel: it is faster there (few taps) and its round-to-nearest partial sums keep the
   // result as accurate as the fp32 reference; the TMEM accumulator truncates.
-  if (precision == 1 && !xview) {
-    int rc = conv_wgrad_shift_try(X, dY, Ymask, dW, dbias, N, s, workspace, workspace_bytes, st);
+  if (precision == 1) {
+    int rc = conv_wgrad_shift_try(X, xview, dY, Ymask, dW, dbias, N, s, workspace, workspace_bytes, st);
     if (rc != 1) return rc;
   }
   if (precision != 0 && !Ymask && s->Cin > 4) {
