@@ -29,6 +29,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <type_traits>
 
 #include "tc_core.cuh"
 
@@ -45,6 +46,8 @@ constexpr int WG_NSLOT = 4;
 constexpr int WG_N = 32;                     // output channels per launch
 constexpr int WG_NACC = 3 * WG_N;            // TMEM columns of one accumulator set (kx = 0, 1, 2)
 constexpr int WG_ROWB = 128;                 // bytes of one position row (32 slots)
+// descriptor high word: SBO = 512 B (4 rows), version 1, base offset 0, SWIZZLE_128B_BASE32B (= 1)
+constexpr uint32_t WG_DESC_HI = (512u >> 4) | (1u << 14) | (1u << 29);
 static_assert(WG_DRAIN0 % 4 == 0, "drain warps must start at a multiple of 4");
 
 struct WgShiftParams {
@@ -64,6 +67,8 @@ struct WgShiftParams {
   int xrows;             // source rows of a full band (Rb + 2 for stride 1, 2 Rb + 1 for stride 2)
   int Rb, nbands, rpc;   // band height, bands per image, rows per accumulator chunk
   int n0;                // first output channel of this launch
+  int ncgo_valid;        // channel groups of dY present in this launch (<= 8)
+  int inv_ncgx, inv_ncgo; // ceil(65536 / n): task / n == (task * inv) >> 16 for the small task counts here
   int mrows;             // MMA M (64 or 128)
   int a_lbo;             // bytes between the M atoms of A
   int x_half, x_buf;     // bytes of one hi copy / one buffer of the X band
@@ -162,10 +167,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
     // ---------------- producers ----------------
     const int xplane = p.H * p.W, oplane = p.OH * p.OW;
     const int ncgx = p.Cin >> 2;
+    // lane constants of the X / dY unit mapping (float4 group gi of task slot sub)
+    const int ngx = p.S == 1 ? (p.OWc >> 2) + 2 : (p.OWc >> 1) + 1;   // float4 groups covering a source row chunk
+    const int tpwx = 32 / ngx, subx = lane / ngx, gix = lane - subx * ngx;
+    const int XN = p.S == 1 ? p.OWc + 2 : 2 * p.OWc + 1;              // source columns needed
+    int poffx[4];                                                     // position of pixel j inside its plane row(s)
+    bool pvx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int xp = 4 * gix + j - 3;                                 // the first group starts 3 columns early
+      pvx[j] = subx < tpwx && xp >= 0 && xp < XN;
+      poffx[j] = p.S == 1 ? xp : (xp & 1) * p.PWx + (xp >> 1);
+    }
+    const int ngo = p.OWc >> 2, tpwo = 32 / ngo, subo = lane / ngo, gio = lane - subo * ngo;
     StageRing ring(2);
     for (int item = first_item; item < nitems; item += item_step, ring.next()) {
       const WgItem it = item_of(item);
       mbar_wait_relaxed(&band_empty[ring.s], ring.par ^ 1);
+      if (!(p.dbg & 4)) {
       if (p.pack3) {
         // --- first layer: <= 4 channels, f32 tensor or uint8 ring view; a row's pixel goes to
         //     chunk ky of row r - ky (ky = 0, 1, 2) ---
@@ -228,25 +247,17 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         }
       } else {
       // --- X band.  A lane converts 4 consecutive pixels (one float4 per channel) of 4 channels. ---
-
         uint8_t* buf = xb + (size_t)ring.s * p.x_buf;
-        const uint32_t buf_a = smem_u32(buf);
         const float4* simg = reinterpret_cast<const float4*>(p.x + (long long)it.img * p.Cin * xplane);
-        // source columns needed: x in [xs, xe); covered by float4 groups g0 .. g0 + ng
-        const int xs = p.S == 1 ? it.c0 - 1 : 2 * it.c0 - 1;
-        const int xe = p.S == 1 ? it.c0 + p.OWc + 1 : 2 * (it.c0 + p.OWc);
-        const int g0 = (xs < 0 ? xs - 3 : xs) / 4;                 // floor(xs / 4)
-        const int ng = (xe + 3) / 4 - g0;
-        const int tpw = 32 / ng > 0 ? 32 / ng : 1;
-        const int sub = lane / ng, gi = lane - sub * ng;
+        const int x4 = 4 * (((p.S * it.c0) >> 2) - 1 + gix);           // first source column of this lane's group
+        const bool okx = (unsigned)x4 < (unsigned)p.W;
         const int nrow = p.S == 1 ? it.rows + 2 : 2 * it.rows + 1;     // source rows of the band
         const int ntask = nrow * ncgx;
-        for (int task = warp * tpw + sub; task < ntask; task += WG_PROD * tpw) {
-          if (sub >= tpw) continue;
-          const int r = task / ncgx, cg = task - r * ncgx;
+        for (int task = warp * tpwx + subx; task < ntask; task += WG_PROD * tpwx) {
+          if (subx >= tpwx) continue;
+          const int r = (task * p.inv_ncgx) >> 16, cg = task - r * ncgx;
           const int sy = p.S * it.r0 + r - 1;
-          const int x4 = 4 * (g0 + gi);
-          const bool ok = (unsigned)sy < (unsigned)p.H && (unsigned)x4 < (unsigned)p.W;
+          const bool ok = okx && (unsigned)sy < (unsigned)p.H;
           const int e0 = ok ? ((cg * 4 * xplane + sy * p.W + x4) >> 2) : 0;
           const int pl4 = ok ? xplane >> 2 : 0;
           float4 v0 = __ldg(simg + e0), v1 = __ldg(simg + e0 + pl4), v2 = __ldg(simg + e0 + 2 * pl4),
@@ -254,19 +265,23 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
           if (!ok) v0 = v1 = v2 = v3 = make_float4(0.f, 0.f, 0.f, 0.f);
           const float px[4][4] = {{v0.x, v1.x, v2.x, v3.x}, {v0.y, v1.y, v2.y, v3.y},
                                   {v0.z, v1.z, v2.z, v3.z}, {v0.w, v1.w, v2.w, v3.w}};
+          const int rowpos = p.ncx * r * p.PWx;                        // stride 2: two parity planes per source row
+          const uint32_t c16 = ((uint32_t)cg & 1u) << 4, c32 = (uint32_t)cg >> 1;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int xp = x4 + j - xs;                           // 0-based inside the needed range
-            if (xp < 0 || x4 + j >= xe) continue;
-            int prow, c;                                          // plane row, column inside it
-            if (p.S == 1) { prow = r; c = xp; }
-            else { prow = r * 2 + (xp & 1); c = xp >> 1; }        // x' = x + 1 = 2 * (c0 + c) + parity
-            const uint32_t off = (uint32_t)(prow * p.PWx + c) * WG_ROWB;
-            wg_store_split(buf + off + wg_swz(buf_a + off, cg), p.x_half, px[j][0], px[j][1], px[j][2], px[j][3]);
-            if (p.pack2 && r > 0) {                               // same pixel as the "row below" of the previous row
-              const uint32_t off2 = off - (uint32_t)p.PWx * WG_ROWB;
-              wg_store_split(buf + off2 + wg_swz(buf_a + off2, cg + 4), p.x_half, px[j][0], px[j][1], px[j][2],
-                             px[j][3]);
+            if (!pvx[j]) continue;
+            const uint32_t pos = (uint32_t)(rowpos + poffx[j]);
+            const float4 h = make_float4(tf32_rna(px[j][0]), tf32_rna(px[j][1]), tf32_rna(px[j][2]), tf32_rna(px[j][3]));
+            const float4 l = make_float4(px[j][0] - h.x, px[j][1] - h.y, px[j][2] - h.z, px[j][3] - h.w);
+            // buffers are 1024-byte aligned: the swizzle phase of a row is its position & 3
+            uint8_t* d = buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16);
+            *reinterpret_cast<float4*>(d) = h;
+            *reinterpret_cast<float4*>(d + p.x_half) = l;
+            if (p.pack2 && r > 0) {                                    // also the "row below" of the previous band row
+              const uint32_t pos2 = pos - (uint32_t)p.PWx;
+              uint8_t* d2 = buf + pos2 * WG_ROWB + ((((c32 + 2u) ^ (pos2 & 3u)) << 5) | c16);
+              *reinterpret_cast<float4*>(d2) = h;
+              *reinterpret_cast<float4*>(d2 + p.x_half) = l;
             }
           }
         }
@@ -274,19 +289,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
       // --- dY band (masked) ---
       {
         uint8_t* buf = ob + (size_t)ring.s * p.o_buf;
-        const uint32_t buf_a = smem_u32(buf);
         const float4* simg = reinterpret_cast<const float4*>(p.dy + ((long long)it.img * p.Cout + p.n0) * oplane);
         const float4* mimg =
             p.mask ? reinterpret_cast<const float4*>(p.mask + ((long long)it.img * p.Cout + p.n0) * oplane) : nullptr;
-        const int ng = p.OWc >> 2, tpw = 32 / ng;
-        const int sub = lane / ng, gi = lane - sub * ng;
-        const int ncg_valid = min(WG_N / 4, (p.Cout - p.n0) >> 2);
-        const int ntask = it.rows * ncg_valid;
-        for (int task = warp * tpw + sub; task < ntask; task += WG_PROD * tpw) {
-          if (sub >= tpw) continue;
-          const int jj = task / ncg_valid, cg = task - jj * ncg_valid;
-          const int e0 = (cg * 4 * oplane + (it.r0 + jj) * p.OW + it.c0 + 4 * gi) >> 2;
-          const int pl4 = oplane >> 2;
+        const int ntask = it.rows * p.ncgo_valid;
+        const int pl4 = oplane >> 2;
+        for (int task = warp * tpwo + subo; task < ntask; task += WG_PROD * tpwo) {
+          if (subo >= tpwo) continue;
+          const int jj = (task * p.inv_ncgo) >> 16, cg = task - jj * p.ncgo_valid;
+          const int e0 = ((cg * 4 * oplane + (it.r0 + jj) * p.OW + it.c0) >> 2) + gio;
           float4 v0 = __ldg(simg + e0), v1 = __ldg(simg + e0 + pl4), v2 = __ldg(simg + e0 + 2 * pl4),
                  v3 = __ldg(simg + e0 + 3 * pl4);
           if (mimg) {
@@ -299,12 +310,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
           }
           const float px[4][4] = {{v0.x, v1.x, v2.x, v3.x}, {v0.y, v1.y, v2.y, v3.y},
                                   {v0.z, v1.z, v2.z, v3.z}, {v0.w, v1.w, v2.w, v3.w}};
+          const uint32_t pos0 = (uint32_t)(jj * p.PWo + 4 * gio);
+          const uint32_t c16 = ((uint32_t)cg & 1u) << 4, c32 = (uint32_t)cg >> 1;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t off = (uint32_t)(jj * p.PWo + 4 * gi + j) * WG_ROWB;
-            wg_store_split(buf + off + wg_swz(buf_a + off, cg), p.o_half, px[j][0], px[j][1], px[j][2], px[j][3]);
+            const uint32_t pos = pos0 + j;
+            uint8_t* d = buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16);
+            wg_store_split(d, p.o_half, px[j][0], px[j][1], px[j][2], px[j][3]);
           }
         }
+      }
       }
       fence_proxy_async();
       __syncwarp();
@@ -313,12 +328,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
   } else if (warp >= WG_MMA && warp < WG_MMA + WG_NISS) {
     // ---------------- MMA issuers (chunks dealt round-robin) ----------------
     const uint32_t me = (uint32_t)(warp - WG_MMA);
-    const uint32_t idesc = make_idesc_mn(p.mrows, WG_N);
     // descriptor low word: start address >> 4 | LBO >> 4 << 16; high word: SBO = 512 B (4 rows),
     // version 1, base offset 0, layout SWIZZLE_128B_BASE32B (= 1)
     const uint32_t a_w0 = ((smem_u32(xb) & 0x3FFFFu) >> 4) | (((uint32_t)p.a_lbo >> 4) << 16);
     const uint32_t b_w0 = ((smem_u32(ob) & 0x3FFFFu) >> 4) | ((512u >> 4) << 16);
-    const uint32_t hi_const = (512u >> 4) | (1u << 14) | (1u << 29);
     const uint32_t xbuf16 = (uint32_t)p.x_buf >> 4, xhalf16 = (uint32_t)p.x_half >> 4;
     const uint32_t obuf16 = (uint32_t)p.o_buf >> 4, ohalf16 = (uint32_t)p.o_half >> 4;
     const uint32_t xrow16 = (uint32_t)(p.S * p.ncx * p.PWx) * (WG_ROWB >> 4);   // 16-byte units per output row of X
@@ -337,33 +350,39 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         if ((ccount & (WG_NISS - 1)) != me) continue;
         mbar_wait(&acc_empty[ab], aphase ^ 1u);
         tc_fence_after();
-        if (elect_one()) {
+        if (!(p.dbg & 2) && elect_one()) {
           const uint32_t tmem_d = tmem_base + ab * WG_NACC;
           const int j1 = min(it.rows, j0 + p.rpc);
-          uint32_t acc = 0;
-          for (int jj = j0; jj < j1; ++jj) {
-            uint32_t a_row = a_buf + (uint32_t)jj * xrow16;
-            uint32_t b_row = b_buf + (uint32_t)jj * orow16;
-            for (int kk = 0; kk < ksteps; ++kk) {
+          // idesc / descriptor high word as immediates (uniform-register issue loop, see mma_tf32_imm)
+          auto issue = [&](auto mtag) {
+            constexpr uint32_t ID = make_idesc_mn(decltype(mtag)::value, WG_N);
+            uint32_t acc = 0;
+            for (int jj = j0; jj < j1; ++jj) {
+              uint32_t a_row = a_buf + (uint32_t)jj * xrow16;
+              uint32_t b_row = b_buf + (uint32_t)jj * orow16;
+              for (int kk = 0; kk < ksteps; ++kk) {
 #pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                // stride 1: row x0 + kx; stride 2: parity plane kx & 1, row x0 + (kx >> 1)
-                const uint32_t a_hi = a_row + (p.ncx == 1 ? (uint32_t)kx : (uint32_t)((kx & 1) * p.PWx + (kx >> 1))) * 8u;
-                // (measured: the swizzle phase comes from the absolute address bits, so a start that is
-                //  not aligned to the 512-byte pattern needs NO base offset in the descriptor)
-                if (p.nsplit == 2) {
-                  mma_tf32_w(tmem_d + kx * WG_N, a_hi + xhalf16, hi_const, b_row, hi_const, idesc, acc);
-                  mma_tf32_w(tmem_d + kx * WG_N, a_hi, hi_const, b_row + ohalf16, hi_const, idesc, 1u);
-                } else {
-                  mma_tf32_w(tmem_d + kx * WG_N, a_hi, hi_const, b_row + ohalf16, hi_const, idesc, acc);
+                for (int kx = 0; kx < 3; ++kx) {
+                  // stride 1: row x0 + kx; stride 2: parity plane kx & 1, row x0 + (kx >> 1)
+                  const uint32_t a_hi = a_row + (p.ncx == 1 ? (uint32_t)kx : (uint32_t)((kx & 1) * p.PWx + (kx >> 1))) * 8u;
+                  // (measured: the swizzle phase comes from the absolute address bits, so a start that is
+                  //  not aligned to the 512-byte pattern needs NO base offset in the descriptor)
+                  if (p.nsplit == 2) {
+                    mma_tf32_imm<ID, WG_DESC_HI>(tmem_d + kx * WG_N, a_hi + xhalf16, b_row, acc);
+                    mma_tf32_imm<ID, WG_DESC_HI>(tmem_d + kx * WG_N, a_hi, b_row + ohalf16, 1u);
+                  } else {
+                    mma_tf32_imm<ID, WG_DESC_HI>(tmem_d + kx * WG_N, a_hi, b_row + ohalf16, acc);
+                  }
+                  mma_tf32_imm<ID, WG_DESC_HI>(tmem_d + kx * WG_N, a_hi, b_row, 1u);
                 }
-                mma_tf32_w(tmem_d + kx * WG_N, a_hi, hi_const, b_row, hi_const, idesc, 1u);
+                acc = 1u;
+                a_row += 8 * 8;
+                b_row += 8 * 8;
               }
-              acc = 1u;
-              a_row += 8 * 8;
-              b_row += 8 * 8;
             }
-          }
+          };
+          if (p.mrows == 64) issue(std::integral_constant<int, 64>{});
+          else issue(std::integral_constant<int, 128>{});
         }
         __syncwarp();
         if (elect_one()) mma_commit(&acc_full[ab]);
@@ -527,6 +546,7 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   p.x = xview ? nullptr : X; p.dy = dY; p.mask = Ymask; p.N = N; p.Cin = s->Cin; p.H = s->H; p.W = s->W;
   if (xview) { p.view = *xview; p.use_view = 1; }
   p.pack3 = first ? 1 : 0;
+  { const int ncgx = first ? 1 : s->Cin / 4; p.inv_ncgx = (65536 + ncgx - 1) / ncgx; }
   p.nsplit = xview ? 1 : 2;
   p.Cout = s->Cout; p.OH = s->OH; p.OW = s->OW; p.S = S; p.ncx = S;
   // column chunks of at most 40 (stride 2: 20) output positions (multiple of 4) that tile the row exactly
@@ -544,6 +564,7 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   // rows per accumulator chunk: a TMEM chain of at most ~64 MMAs (3 per k-step)
   const int ksteps = p.PWo / 8;
   p.rpc = 20 / ksteps;
+  if (p.rpc > p.Rb / tc::WG_NISS) p.rpc = p.Rb / tc::WG_NISS;   // and every issuer warp gets a share of each band
   if (p.rpc < 1) p.rpc = 1;
   double* bias_acc = reinterpret_cast<double*>(workspace);
   p.partial = reinterpret_cast<float*>(bias_acc + ((s->Cout + 1) & ~1));
@@ -559,6 +580,8 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   if (grid > items) grid = items;
   for (int n0 = 0; n0 < s->Cout; n0 += tc::WG_N) {
     p.n0 = n0;
+    p.ncgo_valid = (s->Cout - n0 < tc::WG_N ? s->Cout - n0 : tc::WG_N) / 4;
+    p.inv_ncgo = (65536 + p.ncgo_valid - 1) / p.ncgo_valid;
     kern<<<grid, tc::WG_THREADS, tc::wg_smem_bytes(p), st>>>(p);
     g_launches++;
     A2C_LAUNCH_CHECK();
