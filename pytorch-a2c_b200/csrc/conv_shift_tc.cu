@@ -74,7 +74,7 @@ struct ShiftParams {
   float* out;
   int OutH, OutW;
   int half_bytes, buf_bytes, w_half_bytes, nbuf;
-  int dbg;
+  int dbg;                // A2C_SHIFT_DBG, stage isolation for profiling: 2 = no MMAs, 4 = no loads, 8 = no stores
 };
 
 // no-swizzle K-major descriptor: 8-row groups SBO bytes apart, the two 16-byte k chunks LBO apart
@@ -475,7 +475,6 @@ static int shift_run(ShiftParams& p, FillTaps fill, cudaStream_t st) {
     if (!tc::shift_plan(&p, npad)) continue;
     if (!fill(p)) return 1;
     { const char* e = getenv("A2C_SHIFT_DBG"); p.dbg = e ? atoi(e) : 0; }
-    if (p.dbg & 64) p.nch = 1;
     for (int n0 = 0; n0 < p.J; n0 += npad) {
       p.n0 = n0;
       int rc = npad == 64 ? tc::shift_launch<64>(p, st) : npad == 32 ? tc::shift_launch<32>(p, st)

@@ -74,7 +74,7 @@ struct WgShiftParams {
   int x_half, x_buf;     // bytes of one hi copy / one buffer of the X band
   int o_half, o_buf;     // same for the dY band
   float* partial;        // [grid][128][WG_NACC]
-  int dbg;
+  int dbg;               // A2C_WG_DBG, stage isolation for profiling: 2 = no MMAs, 4 = no producer work
 };
 
 // byte offset of 16-byte chunk j of the position row at byte address row_addr (bands 1024-byte aligned)

@@ -322,7 +322,10 @@ def test_gemm_tcgen05(dev, M, N, K, ta, tb, precision, tol):
 CONVS = [  # Cin, Cout, H, K, stride, pad  -- every layer shape of the four models
     (2, 16, 80, 3, 1, 1), (16, 24, 80, 3, 1, 1), (24, 32, 80, 3, 2, 1), (32, 64, 40, 3, 2, 1),
     (16, 24, 80, 3, 2, 1), (24, 32, 40, 3, 2, 1), (32, 48, 20, 3, 2, 1), (48, 64, 10, 3, 2, 1),
-    (2, 16, 80, 8, 4, 0), (16, 32, 19, 4, 2, 0), (3, 16, 80, 3, 1, 1)]
+    (2, 16, 80, 8, 4, 0), (16, 32, 19, 4, 2, 0), (3, 16, 80, 3, 1, 1),
+    # further paths of the shift-GEMM kernels: unpacked stride-1 weight gradient (M = 128),
+    # 8-channel packed band, single column chunk, narrow images
+    (24, 32, 40, 3, 1, 1), (8, 16, 20, 3, 1, 1), (32, 24, 24, 3, 1, 1), (4, 8, 16, 3, 1, 1)]
 
 
 @pytest.fixture
