@@ -117,7 +117,7 @@ __device__ __forceinline__ void store_weights(const Frag<BN / 4>& f, uint8_t* hi
 template <int BN, bool SPLIT3>
 struct ConvFwdProblem {
   using Params = ConvParams;
-  static constexpr int NA = 8, NB = 4, KC = 8;
+  static constexpr int NA = 8, NB = 4, KC = 8, DEPTH = 1;
   using AState = XRow;
   static __device__ __forceinline__ void init(const Params& p, uint8_t* scratch, int tid, int nt) {
     uint32_t* tab = reinterpret_cast<uint32_t*>(scratch);
@@ -192,7 +192,7 @@ struct DgradRow {
 template <int BN, bool SPLIT3>
 struct ConvDgradProblem {
   using Params = ConvParams;
-  static constexpr int NA = 8, NB = 4, KC = 8;
+  static constexpr int NA = 8, NB = 4, KC = 8, DEPTH = 1;
   using AState = DgradRow;
   static __device__ __forceinline__ void init(const Params& p, uint8_t* scratch, int tid, int nt) {
     uint32_t* tab = reinterpret_cast<uint32_t*>(scratch);
@@ -270,7 +270,7 @@ struct ConvWgradProblem {
   using Params = ConvParams;
   // short TMEM chains: the reduction runs over millions of cancelling terms, and the
   // accumulator's truncation is a bias, not noise (see tc_core.cuh)
-  static constexpr int NA = 8, NB = 4, KC = 2;
+  static constexpr int NA = 8, NB = 4, KC = 2, DEPTH = 1;
   struct AState {};
   static __device__ __forceinline__ void init(const Params& p, uint8_t* scratch, int tid, int nt) {
     uint32_t* tab = reinterpret_cast<uint32_t*>(scratch);   // one entry per tap row of the layer

@@ -33,11 +33,11 @@ struct GemmParams {
   int nkb, kb_per_split;
 };
 
-constexpr int PROD_THREADS = 128;   // 4 producer warps per operand
+constexpr int PROD_THREADS = 256;   // 8 producer warps per operand
 
 template <int ROWS>
 struct GemmFrag {
-  float4 v[ROWS / 16];     // ROWS x 32 fp32 spread over 128 producer threads
+  float4 v[4];             // ROWS (<= 128) x 32 fp32 spread over 256 producer threads
 };
 
 // Load phase: global -> registers.  t = thread index within the operand's producers.
@@ -47,27 +47,23 @@ __device__ __forceinline__ void gemm_load(const GemmOperand& op, int MN, int K, 
   if (op.mode == 0) {
     // k contiguous: unit = (row, 16-byte chunk); a quarter-warp covers one row's 128 bytes
 #pragma unroll
-    for (int i = 0; i < ROWS / 16; ++i) {
+    for (int i = 0; i < 4; ++i) {
       const int u = i * PROD_THREADS + t, row = u >> 3, chunk = u & 7;
       const int mn = mn0 + row, k = k0 + chunk * 4;
       f.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (mn < MN && k < K) f.v[i] = __ldg(reinterpret_cast<const float4*>(op.p + (long long)mn * op.s_mn + k));
+      if (row < ROWS && mn < MN && k < K)
+        f.v[i] = __ldg(reinterpret_cast<const float4*>(op.p + (long long)mn * op.s_mn + k));
     }
   } else {
     // mn contiguous: unit = (group of 4 rows, k-chunk): 4 loads along mn (transposed at store time)
-    constexpr int ITERS = (ROWS / 16 + 3) / 4;
+    const int g = t >> 3, chunk = t & 7;
+    const int mn = mn0 + g * 4;
 #pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const int g = i * (PROD_THREADS / 8) + (t >> 3), chunk = t & 7;
-      const int mn = mn0 + g * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (i * 4 + j >= ROWS / 16) break;
-        const int k = k0 + chunk * 4 + j;
-        f.v[i * 4 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g * 4 < ROWS && mn < MN && k < K)
-          f.v[i * 4 + j] = __ldg(reinterpret_cast<const float4*>(op.p + (long long)k * op.s_k + mn));
-      }
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + chunk * 4 + j;
+      f.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g * 4 < ROWS && mn < MN && k < K)
+        f.v[j] = __ldg(reinterpret_cast<const float4*>(op.p + (long long)k * op.s_k + mn));
     }
   }
 }
@@ -78,23 +74,18 @@ __device__ __forceinline__ void gemm_store(const GemmOperand& op, const GemmFrag
                                            uint8_t* lo, int t) {
   if (op.mode == 0) {
 #pragma unroll
-    for (int i = 0; i < ROWS / 16; ++i) {
+    for (int i = 0; i < 4; ++i) {
       const int u = i * PROD_THREADS + t;
-      store_chunk<SPLIT3>(hi, lo, u >> 3, u & 7, f.v[i]);
+      if ((u >> 3) < ROWS) store_chunk<SPLIT3>(hi, lo, u >> 3, u & 7, f.v[i]);
     }
   } else {
-    constexpr int ITERS = (ROWS / 16 + 3) / 4;
-#pragma unroll
-    for (int i = 0; i < ITERS; ++i) {
-      const int g = i * (PROD_THREADS / 8) + (t >> 3), chunk = t & 7;
-      if (g * 4 >= ROWS) break;
-      if constexpr (ROWS / 16 >= 4) {
-        const float4* v = &f.v[i * 4];
-        store_chunk<SPLIT3>(hi, lo, g * 4 + 0, chunk, make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
-        store_chunk<SPLIT3>(hi, lo, g * 4 + 1, chunk, make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
-        store_chunk<SPLIT3>(hi, lo, g * 4 + 2, chunk, make_float4(v[0].z, v[1].z, v[2].z, v[3].z));
-        store_chunk<SPLIT3>(hi, lo, g * 4 + 3, chunk, make_float4(v[0].w, v[1].w, v[2].w, v[3].w));
-      }
+    const int g = t >> 3, chunk = t & 7;
+    if (g * 4 < ROWS) {
+      const float4* v = f.v;
+      store_chunk<SPLIT3>(hi, lo, g * 4 + 0, chunk, make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
+      store_chunk<SPLIT3>(hi, lo, g * 4 + 1, chunk, make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
+      store_chunk<SPLIT3>(hi, lo, g * 4 + 2, chunk, make_float4(v[0].z, v[1].z, v[2].z, v[3].z));
+      store_chunk<SPLIT3>(hi, lo, g * 4 + 3, chunk, make_float4(v[0].w, v[1].w, v[2].w, v[3].w));
     }
   }
 }
@@ -102,10 +93,11 @@ __device__ __forceinline__ void gemm_store(const GemmOperand& op, const GemmFrag
 template <int BN, bool SPLIT3>
 struct GemmProblem {
   using Params = GemmParams;
-  static constexpr int NA = 4, NB = 4, KC = 8;
+  // 16 producer warps, loads two k-blocks ahead: 64 KB of operand loads in flight per SM
+  static constexpr int NA = 8, NB = 8, KC = 8, DEPTH = 2;
   struct AState {};
   using AFrag = GemmFrag<TM>;
-  using BFrag = GemmFrag<(BN < 64 ? 64 : BN)>;   // at least 4 float4 so the transposing path has a full unit
+  using BFrag = GemmFrag<BN>;
   static __device__ __forceinline__ void init(const Params&, uint8_t*, int, int) {}
   static __device__ __forceinline__ void a_setup(const Params&, const uint8_t*, int, int, AState&) {}
   static __device__ __forceinline__ void load_a(const Params& p, const AState&, const uint8_t*, int m0, int kb,
@@ -116,60 +108,10 @@ struct GemmProblem {
     gemm_store<TM, SPLIT3>(p.A, f, hi, lo, t);
   }
   static __device__ __forceinline__ void load_b(const Params& p, const uint8_t*, int n0, int kb, int t, BFrag& f) {
-    gemm_load_b(p, n0, kb, t, f);
+    gemm_load<BN>(p.B, p.N, p.K, n0, kb * KB, t, f);
   }
   static __device__ __forceinline__ void store_b(const Params& p, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
-    gemm_store_b(p, f, hi, lo, t);
-  }
-  // B tiles narrower than 64 rows: only the first BN rows exist; rows >= BN are never stored
-  static __device__ __forceinline__ void gemm_load_b(const Params& p, int n0, int kb, int t, BFrag& f) {
-    if constexpr (BN >= 64) {
-      gemm_load<BN>(p.B, p.N, p.K, n0, kb * KB, t, f);
-    } else {
-      // BN == 32: 256 chunks (mode 0) or 64 transposing units (mode 1) for 128 threads
-      const GemmOperand& op = p.B;
-      const int k0 = kb * KB;
-      if (op.mode == 0) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int u = i * PROD_THREADS + t, row = u >> 3, chunk = u & 7;
-          const int mn = n0 + row, k = k0 + chunk * 4;
-          f.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (mn < p.N && k < p.K) f.v[i] = __ldg(reinterpret_cast<const float4*>(op.p + (long long)mn * op.s_mn + k));
-        }
-      } else {
-        const int g = t >> 3, chunk = t & 7, mn = n0 + g * 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = k0 + chunk * 4 + j;
-          f.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g * 4 < BN && mn < p.N && k < p.K)
-            f.v[j] = __ldg(reinterpret_cast<const float4*>(op.p + (long long)k * op.s_k + mn));
-        }
-      }
-    }
-  }
-  static __device__ __forceinline__ void gemm_store_b(const Params& p, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
-    if constexpr (BN >= 64) {
-      gemm_store<BN, SPLIT3>(p.B, f, hi, lo, t);
-    } else {
-      if (p.B.mode == 0) {
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int u = i * PROD_THREADS + t;
-          store_chunk<SPLIT3>(hi, lo, u >> 3, u & 7, f.v[i]);
-        }
-      } else {
-        const int g = t >> 3, chunk = t & 7;
-        if (g * 4 < BN) {
-          const float4* v = f.v;
-          store_chunk<SPLIT3>(hi, lo, g * 4 + 0, chunk, make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
-          store_chunk<SPLIT3>(hi, lo, g * 4 + 1, chunk, make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
-          store_chunk<SPLIT3>(hi, lo, g * 4 + 2, chunk, make_float4(v[0].z, v[1].z, v[2].z, v[3].z));
-          store_chunk<SPLIT3>(hi, lo, g * 4 + 3, chunk, make_float4(v[0].w, v[1].w, v[2].w, v[3].w));
-        }
-      }
-    }
+    gemm_store<BN, SPLIT3>(p.B, f, hi, lo, t);
   }
   template <int HALF>
   static __device__ __forceinline__ void epilogue(const Params& p, int row, int nb, const float* acc, int) {

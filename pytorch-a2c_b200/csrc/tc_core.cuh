@@ -29,7 +29,7 @@ constexpr int KB = 32;             // k-block: 32 fp32 = one 128-byte swizzle ro
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int TILE_GROUP_M = 8;     // m-tiles per band of the grouped tile order
 constexpr int SCRATCH_BYTES = 4096;  // per-CTA scratch handed to Problem::init
-constexpr int MAX_THREADS = 704;     // 8 A + 4 B producer warps + 8 drain + MMA + allocator
+constexpr int MAX_THREADS = 800;     // up to 16 producer warps + 8 drain + MMA
 
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -156,6 +156,7 @@ __device__ __forceinline__ void store_elem(uint8_t* hi_tile, uint8_t* lo_tile, i
 // Problem concept:
 //   static constexpr int NA, NB;      producer warps for A / B (NA + NB a multiple of 4)
 //   static constexpr int KC;          k-blocks chained in one TMEM accumulator before it is drained
+//   static constexpr int DEPTH;       k-blocks the producers' global loads run ahead of their stores (1 or 2)
 //   struct Params { ...; int nkb; int kb_per_split; };        (nkb = total k-blocks)
 //   struct AState;                    per-thread, per-m-tile producer state (row decode etc.)
 //   static __device__ void init(const Params&, uint8_t* scratch, int tid, int nthreads);
@@ -165,12 +166,12 @@ __device__ __forceinline__ void store_elem(uint8_t* hi_tile, uint8_t* lo_tile, i
 //   static __device__ void epilogue<HALF>(const Params&, int m, int n_begin, const float* acc, int split);
 // t = thread index within the operand's producer warps.
 template <int BN, bool SPLIT3, class P>
-__global__ void __launch_bounds__(32 * (P::NA + P::NB + NUM_EPI_WARPS + 2), 1)
+__global__ void __launch_bounds__(32 * (P::NA + P::NB + NUM_EPI_WARPS + 1), 1)
 tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
   constexpr int NUM_PROD_WARPS = P::NA + P::NB;
   constexpr int KC = P::KC;
-  constexpr int EPI0 = NUM_PROD_WARPS, MMA_WARP = EPI0 + NUM_EPI_WARPS, ALLOC_WARP = MMA_WARP + 1;
-  constexpr int THREADS = 32 * (ALLOC_WARP + 1);
+  constexpr int EPI0 = NUM_PROD_WARPS, MMA_WARP = EPI0 + NUM_EPI_WARPS, ALLOC_WARP = MMA_WARP;   // the MMA warp owns TMEM
+  constexpr int THREADS = 32 * (MMA_WARP + 1);
   static_assert(NUM_PROD_WARPS % 4 == 0, "drain warps must start at a multiple of 4 (TMEM lane quarters)");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int A_BYTES = TM * 128, B_BYTES = BN * 128;
@@ -233,67 +234,81 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
   auto stage_ptr = [&](int s) { return smem + s * STAGE_BYTES; };
   // stage layout: [A_hi][A_lo?][B_hi][B_lo?]
   if (warp < P::NA) {
-    // ---- A producers: the global loads of k-block i+1 are issued before k-block i is
-    // converted and stored, so their latency overlaps the stage hand-shake and the stores
+    // ---- A producers.  The global loads run P::DEPTH k-blocks ahead of the convert-and-store
+    // step: the producers are latency-bound (bytes in flight = registers holding loads), so the
+    // GEMM uses 16 producer warps with two k-blocks in flight each.
     const int t = threadIdx.x;
-    int tile = tile0, i = 0, it = 0;
     StageRing ring(stages);
-    if (tile < total_tiles && nkb > 0) {
+    if (tile0 < total_tiles && nkb > 0) {
       typename P::AState ast;
-      typename P::AFrag cur, nxt;
-      int mt, nt;
-      tile_of(tile, mt, nt);
-      P::a_setup(p, scratch, mt * TM, t, ast);
-      P::load_a(p, ast, scratch, mt * TM, kb_begin, t, cur);
-      while (true) {
-        int ni = i + 1, ntile = tile, nmt = mt;
-        if (ni == nkb) { ni = 0; ntile = tile + tile_step; }
-        const bool has_next = ntile < total_tiles;
-        if (has_next) {
-          if (ntile != tile) {
-            tile_of(ntile, nmt, nt);
-            if (nmt != mt) P::a_setup(p, scratch, nmt * TM, t, ast);
+      typename P::AFrag f0, f1, f2;
+      int s_tile = tile0, s_i = 0;                       // store cursor (tile, k-block)
+      int l_tile = tile0, l_i = 0, l_mt, l_nt;           // load cursor
+      tile_of(l_tile, l_mt, l_nt);
+      P::a_setup(p, scratch, l_mt * TM, t, ast);
+      auto load_next = [&](typename P::AFrag& f) {
+        if (l_tile >= total_tiles) return;
+        P::load_a(p, ast, scratch, l_mt * TM, kb_begin + l_i, t, f);
+        if (++l_i == nkb) {
+          l_i = 0;
+          l_tile += tile_step;
+          if (l_tile < total_tiles) {
+            int mt2;
+            tile_of(l_tile, mt2, l_nt);
+            if (mt2 != l_mt) { l_mt = mt2; P::a_setup(p, scratch, l_mt * TM, t, ast); }
           }
-          P::load_a(p, ast, scratch, nmt * TM, kb_begin + ni, t, nxt);
         }
+      };
+      load_next(f0);
+      if constexpr (P::DEPTH == 2) load_next(f1);
+      while (s_tile < total_tiles) {
+        if constexpr (P::DEPTH == 2) load_next(f2); else load_next(f1);
         const int s = ring.s;
         mbar_wait(&empty[s], ring.par ^ 1);
         uint8_t* st = stage_ptr(s);
-        P::store_a(p, cur, st, st + A_BYTES, t);
+        P::store_a(p, f0, st, st + A_BYTES, t);
         fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
-        if (!has_next) break;
-        cur = nxt; mt = nmt; tile = ntile; i = ni; ++it; ring.next();
+        f0 = f1;
+        if constexpr (P::DEPTH == 2) f1 = f2;
+        if (++s_i == nkb) { s_i = 0; s_tile += tile_step; }
+        ring.next();
       }
     }
   } else if (warp < NUM_PROD_WARPS) {
-    // ---- B producers (same pipelining; the B tile depends on the k-block only)
+    // ---- B producers (same pipelining; the B tile depends on the k-block and the n tile)
     const int t = (int)threadIdx.x - 32 * P::NA;
-    int tile = tile0, i = 0, it = 0;
     StageRing ring(stages);
-    if (tile < total_tiles && nkb > 0) {
-      typename P::BFrag cur, nxt;
-      int mt, nt;
-      tile_of(tile, mt, nt);
-      P::load_b(p, scratch, nt * BN, kb_begin, t, cur);
-      while (true) {
-        int ni = i + 1, ntile = tile;
-        if (ni == nkb) { ni = 0; ntile = tile + tile_step; }
-        const bool has_next = ntile < total_tiles;
-        if (has_next) {
-          if (ntile != tile) tile_of(ntile, mt, nt);
-          P::load_b(p, scratch, nt * BN, kb_begin + ni, t, nxt);
+    if (tile0 < total_tiles && nkb > 0) {
+      typename P::BFrag f0, f1, f2;
+      int s_tile = tile0, s_i = 0;
+      int l_tile = tile0, l_i = 0, l_mt, l_nt;
+      tile_of(l_tile, l_mt, l_nt);
+      auto load_next = [&](typename P::BFrag& f) {
+        if (l_tile >= total_tiles) return;
+        P::load_b(p, scratch, l_nt * BN, kb_begin + l_i, t, f);
+        if (++l_i == nkb) {
+          l_i = 0;
+          l_tile += tile_step;
+          if (l_tile < total_tiles) tile_of(l_tile, l_mt, l_nt);
         }
+      };
+      load_next(f0);
+      if constexpr (P::DEPTH == 2) load_next(f1);
+      while (s_tile < total_tiles) {
+        if constexpr (P::DEPTH == 2) load_next(f2); else load_next(f1);
         const int s = ring.s;
         mbar_wait(&empty[s], ring.par ^ 1);
         uint8_t* b = stage_ptr(s) + (SPLIT3 ? 2 : 1) * A_BYTES;
-        P::store_b(p, cur, b, b + B_BYTES, t);
+        P::store_b(p, f0, b, b + B_BYTES, t);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
-        if (!has_next) break;
-        cur = nxt; tile = ntile; i = ni; ++it; ring.next();
+        f0 = f1;
+        if constexpr (P::DEPTH == 2) f1 = f2;
+        if (++s_i == nkb) { s_i = 0; s_tile += tile_step; }
+        ring.next();
       }
     }
   } else if (warp == MMA_WARP) {
@@ -410,7 +425,7 @@ int tc_launch(const typename P::Params& p, int mtiles, int ntiles, int splits, c
   if (ncta < 1) ncta = 1;
   if (ncta > mtiles * ntiles) ncta = mtiles * ntiles;
   dim3 grid(ncta, 1, splits);
-  kern<<<grid, 32 * (P::NA + P::NB + NUM_EPI_WARPS + 2), smem, st>>>(p, stages, mtiles, ntiles);
+  kern<<<grid, 32 * (P::NA + P::NB + NUM_EPI_WARPS + 1), smem, st>>>(p, stages, mtiles, ntiles);
   return 0;
 }
 
