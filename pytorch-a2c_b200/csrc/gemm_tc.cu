@@ -40,6 +40,11 @@ struct GemmFrag {
   float4 v[4];             // ROWS (<= 128) x 32 fp32 spread over 256 producer threads
 };
 
+// Transposing path: thread t <-> (group of 4 mn-rows, 16-byte k-chunk).  lane & 7 walks the groups
+// (contiguous in memory), lane >> 3 and the warp index the chunks / higher groups.
+__device__ __forceinline__ int mn_group(int t) { return (t & 7) | (((t >> 5) & 3) << 3); }
+__device__ __forceinline__ int k_chunk(int t) { return ((t >> 3) & 3) | ((t >> 7) << 2); }
+
 // Load phase: global -> registers.  t = thread index within the operand's producers.
 template <int ROWS>
 __device__ __forceinline__ void gemm_load(const GemmOperand& op, int MN, int K, int mn0, int k0, int t,
@@ -55,8 +60,9 @@ __device__ __forceinline__ void gemm_load(const GemmOperand& op, int MN, int K, 
         f.v[i] = __ldg(reinterpret_cast<const float4*>(op.p + (long long)mn * op.s_mn + k));
     }
   } else {
-    // mn contiguous: unit = (group of 4 rows, k-chunk): 4 loads along mn (transposed at store time)
-    const int g = t >> 3, chunk = t & 7;
+    // mn contiguous: unit = (group of 4 rows, k-chunk): 4 loads along mn (transposed at store time).
+    // 8 consecutive lanes take 8 consecutive groups, so a warp load covers 4 k-rows x 128 contiguous bytes
+    const int g = mn_group(t), chunk = k_chunk(t);
     const int mn = mn0 + g * 4;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -79,7 +85,7 @@ __device__ __forceinline__ void gemm_store(const GemmOperand& op, const GemmFrag
       if ((u >> 3) < ROWS) store_chunk<SPLIT3>(hi, lo, u >> 3, u & 7, f.v[i]);
     }
   } else {
-    const int g = t >> 3, chunk = t & 7;
+    const int g = mn_group(t), chunk = k_chunk(t);
     if (g * 4 < ROWS) {
       const float4* v = f.v;
       store_chunk<SPLIT3>(hi, lo, g * 4 + 0, chunk, make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
