@@ -66,6 +66,7 @@ struct WgShiftParams {
   int PWx, PWo;          // positions per X plane row / per dY row (PWo multiple of 8)
   int xrows;             // source rows of a full band (Rb + 2 for stride 1, 2 Rb + 1 for stride 2)
   int Rb, nbands, rpc;   // band height, bands per image, rows per accumulator chunk
+  int pgroups;           // producer groups: 2 = each half of the producer warps fills its own band buffer
   int n0;                // first output channel of this launch
   int ncgo_valid;        // channel groups of dY present in this launch (<= 8)
   int inv_ncgx, inv_ncgo; // ceil(65536 / n): task / n == (task * inv) >> 16 for the small task counts here
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&band_full[b], WG_PROD);
+      mbar_init(&band_full[b], WG_PROD / p.pgroups);
       mbar_init(&band_empty[b], WG_NISS);
     }
     for (int b = 0; b < WG_NSLOT; ++b) {
@@ -180,8 +181,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
       poffx[j] = p.S == 1 ? xp : (xp & 1) * p.PWx + (xp >> 1);
     }
     const int ngo = p.OWc >> 2, tpwo = 32 / ngo, subo = lane / ngo, gio = lane - subo * ngo;
-    StageRing ring(2);
-    for (int item = first_item; item < nitems; item += item_step, ring.next()) {
+    // Layers whose band is a single pass of work for half of the producer warps (few channels)
+    // run two producer groups, group g only ever filling buffer g: the per-band latency chain
+    // (wait, load, convert, store) of consecutive bands then overlaps.
+    const int pgw = WG_PROD / p.pgroups;                    // warps per group
+    const int grp = warp / pgw, pw = warp - grp * pgw;
+    struct { int s; uint32_t par; } ring = {p.pgroups == 2 ? grp : 0, 0u};
+    for (int item = first_item + grp * item_step; item < nitems; item += p.pgroups * item_step) {
       const WgItem it = item_of(item);
       mbar_wait_relaxed(&band_empty[ring.s], ring.par ^ 1);
       if (!(p.dbg & 4)) {
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
           }
         }
         const int nrow = it.rows + 2;
-        for (int r = warp * tpw + sub; r < nrow; r += WG_PROD * tpw) {
+        for (int r = pw * tpw + sub; r < nrow; r += pgw * tpw) {
           if (sub >= tpw) continue;
           const int sy = it.r0 + r - 1;
           const int x4 = 4 * (g0 + gi);
@@ -253,7 +259,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         const bool okx = (unsigned)x4 < (unsigned)p.W;
         const int nrow = p.S == 1 ? it.rows + 2 : 2 * it.rows + 1;     // source rows of the band
         const int ntask = nrow * ncgx;
-        for (int task = warp * tpwx + subx; task < ntask; task += WG_PROD * tpwx) {
+        for (int task = pw * tpwx + subx; task < ntask; task += pgw * tpwx) {
           if (subx >= tpwx) continue;
           const int r = (task * p.inv_ncgx) >> 16, cg = task - r * ncgx;
           const int sy = p.S * it.r0 + r - 1;
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
             p.mask ? reinterpret_cast<const float4*>(p.mask + ((long long)it.img * p.Cout + p.n0) * oplane) : nullptr;
         const int ntask = it.rows * p.ncgo_valid;
         const int pl4 = oplane >> 2;
-        for (int task = warp * tpwo + subo; task < ntask; task += WG_PROD * tpwo) {
+        for (int task = pw * tpwo + subo; task < ntask; task += pgw * tpwo) {
           if (subo >= tpwo) continue;
           const int jj = (task * p.inv_ncgo) >> 16, cg = task - jj * p.ncgo_valid;
           const int e0 = ((cg * 4 * oplane + (it.r0 + jj) * p.OW + it.c0) >> 2) + gio;
@@ -324,6 +330,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&band_full[ring.s]);
+      if (p.pgroups == 2) ring.par ^= 1u;                    // same buffer again, next phase
+      else if ((ring.s ^= 1) == 0) ring.par ^= 1u;           // alternate buffers
     }
   } else if (warp >= WG_MMA && warp < WG_MMA + WG_NISS) {
     // ---------------- MMA issuers (chunks dealt round-robin) ----------------
@@ -566,6 +574,16 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   p.rpc = 20 / ksteps;
   if (p.rpc > p.Rb / tc::WG_NISS) p.rpc = p.Rb / tc::WG_NISS;   // and every issuer warp gets a share of each band
   if (p.rpc < 1) p.rpc = 1;
+  {
+    // two producer groups when half of the warps finish a band's X and dY tasks in one pass
+    const int half = tc::WG_PROD / 2;
+    const int ngx = S == 1 ? p.OWc / 4 + 2 : p.OWc / 2 + 1, ngo = p.OWc / 4;
+    const int tpwx = 32 / ngx > 0 ? 32 / ngx : 1, tpwo = 32 / ngo;
+    const int xtasks = first ? p.Rb + 2 : p.xrows * (s->Cin / 4);
+    const int otasks = p.Rb * ((s->Cout < tc::WG_N ? s->Cout : tc::WG_N) / 4);
+    p.pgroups = (xtasks <= half * tpwx && otasks <= half * tpwo) ? 2 : 1;
+    if (getenv("A2C_WG_PGROUPS")) p.pgroups = atoi(getenv("A2C_WG_PGROUPS")) == 2 ? 2 : 1;
+  }
   double* bias_acc = reinterpret_cast<double*>(workspace);
   p.partial = reinterpret_cast<float*>(bias_acc + ((s->Cout + 1) & ~1));
   { const char* e = getenv("A2C_WG_DBG"); p.dbg = e ? atoi(e) : 0; }
