@@ -66,6 +66,7 @@ struct WgShiftParams {
   int PWx, PWo;          // positions per X plane row / per dY row (PWo multiple of 8)
   int xrows;             // source rows of a full band (Rb + 2 for stride 1, 2 Rb + 1 for stride 2)
   int Rb, nbands, rpc;   // band height, bands per image, rows per accumulator chunk
+  int ones_chunk;        // 16-byte slot chunk of every X row holding the constant 1 (bias gradient row), or -1
   int pgroups;           // producer groups: 2 = each half of the producer warps fills its own band buffer
   int n0;                // first output channel of this launch
   int ncgo_valid;        // channel groups of dY present in this launch (<= 8)
@@ -146,6 +147,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
     // pad positions / pad slots are never written: clear both bands (and the over-read slack) once
     const int nz = (2 * p.x_buf + 2 * p.o_buf + 8192) / 16;
     for (int i = threadIdx.x; i < nz; i += WG_THREADS) reinterpret_cast<uint4*>(xb)[i] = make_uint4(0, 0, 0, 0);
+    if (p.ones_chunk >= 0) {
+      // a free slot chunk of every X row holds 1.0 (hi copy; lo stays 0): that accumulator row becomes
+      // sum(dY) = the bias gradient, for free
+      __syncthreads();
+      const int npos = p.xrows * p.ncx * p.PWx;
+      for (int i = threadIdx.x; i < 2 * npos; i += WG_THREADS) {
+        const int b = i / npos, pos = i - b * npos;
+        uint8_t* d = xb + (size_t)b * p.x_buf + (size_t)pos * WG_ROWB +
+                     (((((uint32_t)p.ones_chunk >> 1) ^ ((uint32_t)pos & 3u)) << 5) | (((uint32_t)p.ones_chunk & 1u) << 4));
+        *reinterpret_cast<float4*>(d) = make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+    }
     fence_proxy_async();
   }
   tc_fence_before();
@@ -442,21 +455,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
 // M = 64 accumulators live in TMEM lanes (m % 16) + 32 * (m / 16).
 __global__ void __launch_bounds__(256)
 wg_shift_reduce_kernel(const float* __restrict__ partial, int grid, int pack, int mrows, int Cin, int Cout,
-                       int n0, float* __restrict__ dW) {
+                       int n0, float* __restrict__ dW, int bias_row, float* __restrict__ dbias) {
   const int nco = min(WG_N, Cout - n0);
-  const int total = nco * Cin * 9;
+  const int nw = nco * Cin * 9;
+  const int total = nw + (dbias && bias_row >= 0 ? nco : 0);
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int kx = e % 3;
+    const bool is_bias = e >= nw;
+    const int kx = is_bias ? 0 : e % 3;
     int r = e / 3;
     const int ky = r % 3;
     r /= 3;
-    const int ci = r % Cin, co = r / Cin;
-    const int m = pack == 3 ? ky * 4 + ci : (pack == 2 ? ky * 16 + ci : ky * 32 + ci);
+    const int ci = r % Cin, co = is_bias ? e - nw : r / Cin;
+    const int m = is_bias ? bias_row : (pack == 3 ? ky * 4 + ci : (pack == 2 ? ky * 16 + ci : ky * 32 + ci));
     const int lane_row = mrows == 128 ? m : (m & 15) + 32 * (m >> 4);
     double s = 0.0;
     for (int b = 0; b < grid; ++b)
       s += (double)partial[((size_t)b * 128 + lane_row) * WG_NACC + kx * WG_N + co];
-    dW[(((size_t)(n0 + co) * Cin + ci) * 3 + ky) * 3 + kx] = (float)s;
+    if (is_bias) dbias[n0 + co] = (float)s;
+    else dW[(((size_t)(n0 + co) * Cin + ci) * 3 + ky) * 3 + kx] = (float)s;
   }
 }
 
@@ -584,6 +600,10 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
     p.pgroups = (xtasks <= half * tpwx && otasks <= half * tpwo) ? 2 : 1;
     if (getenv("A2C_WG_PGROUPS")) p.pgroups = atoi(getenv("A2C_WG_PGROUPS")) == 2 ? 2 : 1;
   }
+  // bias gradient from the MMA when the X rows have a free 4-slot chunk (first layers: chunk 3 of the
+  // packed atom; 20- and 24-channel layers: chunk Cin / 4); otherwise the separate masked sum below
+  p.ones_chunk = first ? 3 : ((!p.pack2 && s->Cin <= 28) ? s->Cin / 4 : -1);
+  const int bias_row = p.ones_chunk >= 0 ? 4 * p.ones_chunk : -1;     // accumulator row (ky = 0 atom)
   double* bias_acc = reinterpret_cast<double*>(workspace);
   p.partial = reinterpret_cast<float*>(bias_acc + ((s->Cout + 1) & ~1));
   { const char* e = getenv("A2C_WG_DBG"); p.dbg = e ? atoi(e) : 0; }
@@ -604,12 +624,12 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
     g_launches++;
     A2C_LAUNCH_CHECK();
     const int nco = s->Cout - n0 < tc::WG_N ? s->Cout - n0 : tc::WG_N;
-    tc::wg_shift_reduce_kernel<<<cdiv(nco * s->Cin * 9, 256), 256, 0, st>>>(p.partial, grid, p.pack3 ? 3 : (p.pack2 ? 2 : 0), p.mrows,
-                                                                            s->Cin, s->Cout, n0, dW);
+    tc::wg_shift_reduce_kernel<<<cdiv(nco * s->Cin * 9 + nco, 256), 256, 0, st>>>(
+        p.partial, grid, p.pack3 ? 3 : (p.pack2 ? 2 : 0), p.mrows, s->Cin, s->Cout, n0, dW, bias_row, dbias);
     g_launches++;
     A2C_LAUNCH_CHECK();
   }
-  if (dbias) {
+  if (dbias && bias_row < 0) {
     A2C_CUDA_CHECK(cudaMemsetAsync(bias_acc, 0, sizeof(double) * s->Cout, st));
     const int hw4 = s->OH * s->OW / 4;
     int bx = (int)cdivll((long long)N * hw4, 256 * 4);
