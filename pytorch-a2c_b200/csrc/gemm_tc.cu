@@ -40,10 +40,14 @@ struct GemmFrag {
   float4 v[4];             // ROWS (<= 128) x 32 fp32 spread over 256 producer threads
 };
 
-// Transposing path: thread t <-> (group of 4 mn-rows, 16-byte k-chunk).  lane & 7 walks the groups
-// (contiguous in memory), lane >> 3 and the warp index the chunks / higher groups.
-__device__ __forceinline__ int mn_group(int t) { return (t & 7) | (((t >> 5) & 3) << 3); }
-__device__ __forceinline__ int k_chunk(int t) { return ((t >> 3) & 3) | ((t >> 7) << 2); }
+// Transposing path: thread t <-> (group of 4 mn-rows, 16-byte k-chunk).  Across a warp the 8 groups
+// are consecutive (a warp load covers 4 k-rows x 128 contiguous bytes); inside every quarter-warp
+// (the unit in which a 128-bit shared store is checked for bank conflicts) the lanes take 2 group
+// parities x 4 chunks, which the 128B swizzle (chunk ^ row & 7, row = 4*group + q) maps to 8
+// different 16-byte bank groups.  (ncu: 74 % of the shared wavefronts of the wgrad GEMM were
+// conflicts with 8 groups x 1 chunk per quarter-warp.)
+__device__ __forceinline__ int mn_group(int t) { return (((t >> 3) & 3) << 1) | (t & 1) | (((t >> 5) & 3) << 3); }
+__device__ __forceinline__ int k_chunk(int t) { return ((t >> 1) & 3) | ((t >> 7) << 2); }
 
 // Load phase: global -> registers.  t = thread index within the operand's producers.
 template <int ROWS>

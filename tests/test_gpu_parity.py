@@ -2,6 +2,7 @@
 reference-generated golden fixtures.  Bit-exact for uint8 / index / scan work,
 <= 1e-5 relative (BASELINE.json north_star) for fp32."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -636,6 +637,8 @@ def test_full_size_update_against_reference_golden(dev, precision_guard, fname, 
         mine = grads[name].cpu().numpy()
         ref_own = H.grad_err_compact(g[key], g64["grad64/" + name], scale)
         e64 = H.grad_err(mine, g64["grad64/" + name], scale)
+        if os.environ.get("A2C_TEST_REPORT"):
+            print("MARGIN %s prec=%d %-28s e64=%.3g ref_own=%.3g ratio=%.2f" % (fname, precision, name, e64, ref_own, e64 / max(TOL / FACT, ref_own)))
         assert e64 <= max(TOL, FACT * ref_own), (name, "vs float64 oracle", e64, "reference's own", ref_own)
         eref = H.grad_err(mine, g[key], scale)
         assert eref <= TOL + (FACT + 2) * ref_own, (name, "vs fp32 reference", eref, ref_own)
