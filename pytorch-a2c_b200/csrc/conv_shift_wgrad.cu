@@ -84,6 +84,12 @@ __device__ __forceinline__ uint32_t wg_swz(uint32_t row_addr, int j) {
   return ((((uint32_t)j >> 1) ^ ((row_addr >> 7) & 3u)) << 5) | (((uint32_t)j & 1u) << 4);
 }
 
+// (v[r], v[r+1], v[r+2], v[r+3]) with indices mod 4: the pixel a lane handles in step j is (j + r) & 3
+__device__ __forceinline__ float4 rot4(float4 v, int r) {
+  const float4 a = (r & 1) ? make_float4(v.y, v.z, v.w, v.x) : v;
+  return (r & 2) ? make_float4(a.z, a.w, a.x, a.y) : a;
+}
+
 __device__ __forceinline__ void wg_store_split(uint8_t* dst, int half_bytes, float a, float b, float c, float d) {
   const float4 h = make_float4(tf32_rna(a), tf32_rna(b), tf32_rna(c), tf32_rna(d));
   *reinterpret_cast<float4*>(dst) = h;
@@ -181,19 +187,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
     // ---------------- producers ----------------
     const int xplane = p.H * p.W, oplane = p.OH * p.OW;
     const int ncgx = p.Cin >> 2;
-    // lane constants of the X / dY unit mapping (float4 group gi of task slot sub)
+    // Lane mapping of the X / dY units.  A task is (row, PAIR of channel groups); inside a task
+    // slot even / odd lanes take the two channel groups, lane >> 1 the float4 group gi along the
+    // row.  A lane holds a 4 pixel x 4 channel block and stores pixel (j + gi) & 3 in step j: the 8
+    // lanes of a quarter-warp (4 consecutive gi x 2 channel groups) then hit 4 swizzle phases x 2
+    // chunk parities = 8 different 16-byte bank groups.  (With all lanes on the same pixel index
+    // and channel group every 128-bit store was an 8-way bank conflict: ncu showed 82 % of the
+    // shared wavefronts as conflicts, 3 ms of shared-memory time per launch of conv2's layer.)
     const int ngx = p.S == 1 ? (p.OWc >> 2) + 2 : (p.OWc >> 1) + 1;   // float4 groups covering a source row chunk
-    const int tpwx = 32 / ngx, subx = lane / ngx, gix = lane - subx * ngx;
+    const int tpwx = 32 / (2 * ngx) > 0 ? 32 / (2 * ngx) : 1;
+    const int subx = lane / (2 * ngx), lx = lane - subx * 2 * ngx, cgpx = lx & 1, gix = lx >> 1;
     const int XN = p.S == 1 ? p.OWc + 2 : 2 * p.OWc + 1;              // source columns needed
-    int poffx[4];                                                     // position of pixel j inside its plane row(s)
-    bool pvx[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int xp = 4 * gix + j - 3;                                 // the first group starts 3 columns early
-      pvx[j] = subx < tpwx && xp >= 0 && xp < XN;
-      poffx[j] = p.S == 1 ? xp : (xp & 1) * p.PWx + (xp >> 1);
-    }
-    const int ngo = p.OWc >> 2, tpwo = 32 / ngo, subo = lane / ngo, gio = lane - subo * ngo;
+    const int npairx = (ncgx + 1) >> 1;
+    const int ngo = p.OWc >> 2, tpwo = 32 / (2 * ngo) > 0 ? 32 / (2 * ngo) : 1;
+    const int subo = lane / (2 * ngo), lo = lane - subo * 2 * ngo, cgpo = lo & 1, gio = lo >> 1;
     // Layers whose band is a single pass of work for half of the producer warps (few channels)
     // run two producer groups, group g only ever filling buffer g: the per-band latency chain
     // (wait, load, convert, store) of consecutive bands then overlaps.
@@ -271,10 +278,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         const int x4 = 4 * (((p.S * it.c0) >> 2) - 1 + gix);           // first source column of this lane's group
         const bool okx = (unsigned)x4 < (unsigned)p.W;
         const int nrow = p.S == 1 ? it.rows + 2 : 2 * it.rows + 1;     // source rows of the band
-        const int ntask = nrow * ncgx;
+        const int ntask = nrow * npairx;
         for (int task = pw * tpwx + subx; task < ntask; task += pgw * tpwx) {
-          if (subx >= tpwx) continue;
-          const int r = (task * p.inv_ncgx) >> 16, cg = task - r * ncgx;
+          const int r = (task * p.inv_ncgx) >> 16, cg = 2 * (task - r * npairx) + cgpx;
+          if (subx >= tpwx || cg >= ncgx) continue;
           const int sy = p.S * it.r0 + r - 1;
           const bool ok = okx && (unsigned)sy < (unsigned)p.H;
           const int e0 = ok ? ((cg * 4 * xplane + sy * p.W + x4) >> 2) : 0;
@@ -282,14 +289,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
           float4 v0 = __ldg(simg + e0), v1 = __ldg(simg + e0 + pl4), v2 = __ldg(simg + e0 + 2 * pl4),
                  v3 = __ldg(simg + e0 + 3 * pl4);
           if (!ok) v0 = v1 = v2 = v3 = make_float4(0.f, 0.f, 0.f, 0.f);
+          v0 = rot4(v0, gix); v1 = rot4(v1, gix); v2 = rot4(v2, gix); v3 = rot4(v3, gix);
           const float px[4][4] = {{v0.x, v1.x, v2.x, v3.x}, {v0.y, v1.y, v2.y, v3.y},
                                   {v0.z, v1.z, v2.z, v3.z}, {v0.w, v1.w, v2.w, v3.w}};
           const int rowpos = p.ncx * r * p.PWx;                        // stride 2: two parity planes per source row
           const uint32_t c16 = ((uint32_t)cg & 1u) << 4, c32 = (uint32_t)cg >> 1;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            if (!pvx[j]) continue;
-            const uint32_t pos = (uint32_t)(rowpos + poffx[j]);
+            const int xp = 4 * gix + ((j + gix) & 3) - 3;              // source column (0-based in the needed range) of this step's pixel
+            if (xp < 0 || xp >= XN) continue;
+            const uint32_t pos = (uint32_t)(rowpos + (p.S == 1 ? xp : (xp & 1) * p.PWx + (xp >> 1)));
             const float4 h = make_float4(tf32_rna(px[j][0]), tf32_rna(px[j][1]), tf32_rna(px[j][2]), tf32_rna(px[j][3]));
             const float4 l = make_float4(px[j][0] - h.x, px[j][1] - h.y, px[j][2] - h.z, px[j][3] - h.w);
             // buffers are 1024-byte aligned: the swizzle phase of a row is its position & 3
@@ -311,11 +320,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         const float4* simg = reinterpret_cast<const float4*>(p.dy + ((long long)it.img * p.Cout + p.n0) * oplane);
         const float4* mimg =
             p.mask ? reinterpret_cast<const float4*>(p.mask + ((long long)it.img * p.Cout + p.n0) * oplane) : nullptr;
-        const int ntask = it.rows * p.ncgo_valid;
+        const int npairo = (p.ncgo_valid + 1) >> 1;
+        const int ntask = it.rows * npairo;
         const int pl4 = oplane >> 2;
         for (int task = pw * tpwo + subo; task < ntask; task += pgw * tpwo) {
-          if (subo >= tpwo) continue;
-          const int jj = (task * p.inv_ncgo) >> 16, cg = task - jj * p.ncgo_valid;
+          const int jj = (task * p.inv_ncgo) >> 16, cg = 2 * (task - jj * npairo) + cgpo;
+          if (subo >= tpwo || cg >= p.ncgo_valid) continue;
           const int e0 = ((cg * 4 * oplane + (it.r0 + jj) * p.OW + it.c0) >> 2) + gio;
           float4 v0 = __ldg(simg + e0), v1 = __ldg(simg + e0 + pl4), v2 = __ldg(simg + e0 + 2 * pl4),
                  v3 = __ldg(simg + e0 + 3 * pl4);
@@ -327,13 +337,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
             v2.x = m2.x > 0.f ? v2.x : 0.f; v2.y = m2.y > 0.f ? v2.y : 0.f; v2.z = m2.z > 0.f ? v2.z : 0.f; v2.w = m2.w > 0.f ? v2.w : 0.f;
             v3.x = m3.x > 0.f ? v3.x : 0.f; v3.y = m3.y > 0.f ? v3.y : 0.f; v3.z = m3.z > 0.f ? v3.z : 0.f; v3.w = m3.w > 0.f ? v3.w : 0.f;
           }
+          v0 = rot4(v0, gio); v1 = rot4(v1, gio); v2 = rot4(v2, gio); v3 = rot4(v3, gio);
           const float px[4][4] = {{v0.x, v1.x, v2.x, v3.x}, {v0.y, v1.y, v2.y, v3.y},
                                   {v0.z, v1.z, v2.z, v3.z}, {v0.w, v1.w, v2.w, v3.w}};
           const uint32_t pos0 = (uint32_t)(jj * p.PWo + 4 * gio);
           const uint32_t c16 = ((uint32_t)cg & 1u) << 4, c32 = (uint32_t)cg >> 1;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t pos = pos0 + j;
+            const uint32_t pos = pos0 + (uint32_t)((j + gio) & 3);
             uint8_t* d = buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16);
             wg_store_split(d, p.o_half, px[j][0], px[j][1], px[j][2], px[j][3]);
           }
@@ -570,7 +581,7 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   p.x = xview ? nullptr : X; p.dy = dY; p.mask = Ymask; p.N = N; p.Cin = s->Cin; p.H = s->H; p.W = s->W;
   if (xview) { p.view = *xview; p.use_view = 1; }
   p.pack3 = first ? 1 : 0;
-  { const int ncgx = first ? 1 : s->Cin / 4; p.inv_ncgx = (65536 + ncgx - 1) / ncgx; }
+  { const int np = first ? 1 : (s->Cin / 4 + 1) / 2; p.inv_ncgx = (65536 + np - 1) / np; }
   p.nsplit = xview ? 1 : 2;
   p.Cout = s->Cout; p.OH = s->OH; p.OW = s->OW; p.S = S; p.ncx = S;
   // column chunks of at most 40 (stride 2: 20) output positions (multiple of 4) that tile the row exactly
@@ -594,9 +605,10 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
     // two producer groups when half of the warps finish a band's X and dY tasks in one pass
     const int half = tc::WG_PROD / 2;
     const int ngx = S == 1 ? p.OWc / 4 + 2 : p.OWc / 2 + 1, ngo = p.OWc / 4;
-    const int tpwx = 32 / ngx > 0 ? 32 / ngx : 1, tpwo = 32 / ngo;
-    const int xtasks = first ? p.Rb + 2 : p.xrows * (s->Cin / 4);
-    const int otasks = p.Rb * ((s->Cout < tc::WG_N ? s->Cout : tc::WG_N) / 4);
+    const int tpwx = first ? (32 / ngx > 0 ? 32 / ngx : 1) : (32 / (2 * ngx) > 0 ? 32 / (2 * ngx) : 1);
+    const int tpwo = 32 / (2 * ngo) > 0 ? 32 / (2 * ngo) : 1;
+    const int xtasks = first ? p.Rb + 2 : p.xrows * ((s->Cin / 4 + 1) / 2);
+    const int otasks = p.Rb * (((s->Cout < tc::WG_N ? s->Cout : tc::WG_N) / 4 + 1) / 2);
     p.pgroups = (xtasks <= half * tpwx && otasks <= half * tpwo) ? 2 : 1;
     if (getenv("A2C_WG_PGROUPS")) p.pgroups = atoi(getenv("A2C_WG_PGROUPS")) == 2 ? 2 : 1;
   }
@@ -619,7 +631,7 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   for (int n0 = 0; n0 < s->Cout; n0 += tc::WG_N) {
     p.n0 = n0;
     p.ncgo_valid = (s->Cout - n0 < tc::WG_N ? s->Cout - n0 : tc::WG_N) / 4;
-    p.inv_ncgo = (65536 + p.ncgo_valid - 1) / p.ncgo_valid;
+    { const int np = (p.ncgo_valid + 1) / 2; p.inv_ncgo = (65536 + np - 1) / np; }
     kern<<<grid, tc::WG_THREADS, tc::wg_smem_bytes(p), st>>>(p);
     g_launches++;
     A2C_LAUNCH_CHECK();
