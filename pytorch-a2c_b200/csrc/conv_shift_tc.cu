@@ -121,6 +121,12 @@ __device__ __forceinline__ BandInfo band_info(const ShiftParams& p, int item) {
   return b;
 }
 
+// (v[r], v[r+1], v[r+2], v[r+3]) with indices mod 4
+__device__ __forceinline__ float4 rot4(float4 v, int r) {
+  const float4 a = (r & 1) ? make_float4(v.y, v.z, v.w, v.x) : v;
+  return (r & 2) ? make_float4(a.z, a.w, a.x, a.y) : a;
+}
+
 __device__ __forceinline__ void store_split(uint8_t* dst, int half_bytes, float a, float b, float c, float d) {
   const float4 h = make_float4(tf32_rna(a), tf32_rna(b), tf32_rna(c), tf32_rna(d));
   *reinterpret_cast<float4*>(dst) = h;
@@ -239,11 +245,17 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
           uint8_t* dst = buf + ((size_t)cg * p.plane_pos + r * p.PW) * 16;
           const int xq = 4 * m + p.p0x;                        // plane x' of pixel 0
           if (p.cs == 1) {
+            // In step j the lane stores pixel (j + rot) & 3 of its 4-pixel block: with every lane on the
+            // same pixel index the 8 lanes of a quarter-warp hit only 2 of the 8 16-byte bank groups
+            // (ncu: ~70 % of the shared wavefronts were conflicts); rotated, their 16-byte units are 8
+            // consecutive residues mod 8.
+            const int rot = (m >> 1) & 3;
+            v0 = rot4(v0, rot); v1 = rot4(v1, rot); v2 = rot4(v2, rot); v3 = rot4(v3, rot);
             dst += (size_t)(p.cls_pos[0] + xq) * 16;
-            store_split(dst, p.half_bytes, v0.x, v1.x, v2.x, v3.x);
-            store_split(dst + 16, p.half_bytes, v0.y, v1.y, v2.y, v3.y);
-            store_split(dst + 32, p.half_bytes, v0.z, v1.z, v2.z, v3.z);
-            store_split(dst + 48, p.half_bytes, v0.w, v1.w, v2.w, v3.w);
+            store_split(dst + ((0 + rot) & 3) * 16, p.half_bytes, v0.x, v1.x, v2.x, v3.x);
+            store_split(dst + ((1 + rot) & 3) * 16, p.half_bytes, v0.y, v1.y, v2.y, v3.y);
+            store_split(dst + ((2 + rot) & 3) * 16, p.half_bytes, v0.z, v1.z, v2.z, v3.z);
+            store_split(dst + ((3 + rot) & 3) * 16, p.half_bytes, v0.w, v1.w, v2.w, v3.w);
           } else {
             const int* cp = p.cls_pos + cy * 2;
             store_split(dst + (size_t)(cp[xq & 1] + (xq >> 1)) * 16, p.half_bytes, v0.x, v1.x, v2.x, v3.x);
