@@ -67,6 +67,7 @@ struct WgShiftParams {
   int xrows;             // source rows of a full band (Rb + 2 for stride 1, 2 Rb + 1 for stride 2)
   int Rb, nbands, rpc;   // band height, bands per image, rows per accumulator chunk
   int ones_chunk;        // 16-byte slot chunk of every X row holding the constant 1 (bias gradient row), or -1
+  int pair_o;            // dY lane mapping: 1 = channel-group pairs on even / odd lanes, 0 = one channel group per task
   int pgroups;           // producer groups: 2 = each half of the producer warps fills its own band buffer
   int n0;                // first output channel of this launch
   int ncgo_valid;        // channel groups of dY present in this launch (<= 8)
@@ -199,8 +200,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
     const int subx = lane / (2 * ngx), lx = lane - subx * 2 * ngx, cgpx = lx & 1, gix = lx >> 1;
     const int XN = p.S == 1 ? p.OWc + 2 : 2 * p.OWc + 1;              // source columns needed
     const int npairx = (ncgx + 1) >> 1;
-    const int ngo = p.OWc >> 2, tpwo = 32 / (2 * ngo) > 0 ? 32 / (2 * ngo) : 1;
-    const int subo = lane / (2 * ngo), lo = lane - subo * 2 * ngo, cgpo = lo & 1, gio = lo >> 1;
+    // (narrow dY, <= 4 channel groups: one group per task keeps more warps busy per band than pairs do)
+    const int ngo = p.OWc >> 2, lpo = p.pair_o ? 2 * ngo : ngo;        // lanes per dY task
+    const int tpwo = 32 / lpo > 0 ? 32 / lpo : 1;
+    const int subo = lane / lpo, lo = lane - subo * lpo;
+    const int cgpo = p.pair_o ? lo & 1 : 0, gio = p.pair_o ? lo >> 1 : lo;
     // Layers whose band is a single pass of work for half of the producer warps (few channels)
     // run two producer groups, group g only ever filling buffer g: the per-band latency chain
     // (wait, load, convert, store) of consecutive bands then overlaps.
@@ -320,11 +324,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         const float4* simg = reinterpret_cast<const float4*>(p.dy + ((long long)it.img * p.Cout + p.n0) * oplane);
         const float4* mimg =
             p.mask ? reinterpret_cast<const float4*>(p.mask + ((long long)it.img * p.Cout + p.n0) * oplane) : nullptr;
-        const int npairo = (p.ncgo_valid + 1) >> 1;
+        const int npairo = p.pair_o ? (p.ncgo_valid + 1) >> 1 : p.ncgo_valid;   // tasks per row
         const int ntask = it.rows * npairo;
         const int pl4 = oplane >> 2;
         for (int task = pw * tpwo + subo; task < ntask; task += pgw * tpwo) {
-          const int jj = (task * p.inv_ncgo) >> 16, cg = 2 * (task - jj * npairo) + cgpo;
+          const int jj = (task * p.inv_ncgo) >> 16;
+          const int cg = p.pair_o ? 2 * (task - jj * npairo) + cgpo : task - jj * npairo;
           if (subo >= tpwo || cg >= p.ncgo_valid) continue;
           const int e0 = ((cg * 4 * oplane + (it.r0 + jj) * p.OW + it.c0) >> 2) + gio;
           float4 v0 = __ldg(simg + e0), v1 = __ldg(simg + e0 + pl4), v2 = __ldg(simg + e0 + 2 * pl4),
@@ -606,9 +611,12 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
     const int half = tc::WG_PROD / 2;
     const int ngx = S == 1 ? p.OWc / 4 + 2 : p.OWc / 2 + 1, ngo = p.OWc / 4;
     const int tpwx = first ? (32 / ngx > 0 ? 32 / ngx : 1) : (32 / (2 * ngx) > 0 ? 32 / (2 * ngx) : 1);
-    const int tpwo = 32 / (2 * ngo) > 0 ? 32 / (2 * ngo) : 1;
+    const int ncgo = (s->Cout < tc::WG_N ? s->Cout : tc::WG_N) / 4;
+    p.pair_o = ncgo > 4 ? 1 : 0;
+    const int lpo = p.pair_o ? 2 * ngo : ngo;
+    const int tpwo = 32 / lpo > 0 ? 32 / lpo : 1;
     const int xtasks = first ? p.Rb + 2 : p.xrows * ((s->Cin / 4 + 1) / 2);
-    const int otasks = p.Rb * (((s->Cout < tc::WG_N ? s->Cout : tc::WG_N) / 4 + 1) / 2);
+    const int otasks = p.Rb * (p.pair_o ? (ncgo + 1) / 2 : ncgo);
     p.pgroups = (xtasks <= half * tpwx && otasks <= half * tpwo) ? 2 : 1;
     if (getenv("A2C_WG_PGROUPS")) p.pgroups = atoi(getenv("A2C_WG_PGROUPS")) == 2 ? 2 : 1;
   }
@@ -631,7 +639,7 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   for (int n0 = 0; n0 < s->Cout; n0 += tc::WG_N) {
     p.n0 = n0;
     p.ncgo_valid = (s->Cout - n0 < tc::WG_N ? s->Cout - n0 : tc::WG_N) / 4;
-    { const int np = (p.ncgo_valid + 1) / 2; p.inv_ncgo = (65536 + np - 1) / np; }
+    { const int np = p.pair_o ? (p.ncgo_valid + 1) / 2 : p.ncgo_valid; p.inv_ncgo = (65536 + np - 1) / np; }
     kern<<<grid, tc::WG_THREADS, tc::wg_smem_bytes(p), st>>>(p);
     g_launches++;
     A2C_LAUNCH_CHECK();
