@@ -55,6 +55,10 @@ struct ShiftClass {       // one output parity class
 struct ShiftParams {
   const float* src;       // f32 [N][C][SH][SW], SW % 4 == 0
   const float* mask;      // optional, same shape: source element counts only where mask > 0
+  a2c_state_view view;    // first-layer source: uint8 plane ring (use_view)
+  int use_view;
+  int cvalid;             // real source channels (first layers: C is padded to 8, channels >= cvalid are zero)
+  int nsplit;             // 2: the source has a lo part (3 MMAs per product); 1: exact in TF32 ({0,1} ring) -> 2 MMAs
   int N, C, SH, SW, ncg, ksteps;
   int cs;                 // input class step (1, or 2 for the stride-2 forward)
   int p0y, p0x;           // plane (row r, col c, class cy,cx) <-> source (r*cs + cy - p0y, c*cs + cx - p0x)
@@ -187,8 +191,9 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int k = ks * 8 + kc * 4 + e;
-        v[e] = (p.n0 + n < p.J) ? __ldg(p.wt + (long long)(p.n0 + n) * p.wsn + (long long)k * p.wsk + p.taps[g].woff)
-                                : 0.0f;
+        v[e] = (p.n0 + n < p.J && k < p.cvalid)
+                   ? __ldg(p.wt + (long long)(p.n0 + n) * p.wsn + (long long)k * p.wsk + p.taps[g].woff)
+                   : 0.0f;
       }
       store_split(wsm + (size_t)(g * p.ksteps + ks) * WBLK + kc * (NPAD * 16) + n * 16, p.w_half_bytes, v[0], v[1],
                   v[2], v[3]);
@@ -221,6 +226,24 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
       uint8_t* buf = bufs + (size_t)ring.s * p.buf_bytes;
       mbar_wait_relaxed(&patch_empty[ring.s], ring.par ^ 1);   // long wait: do not burn issue slots
       const float4* simg = reinterpret_cast<const float4*>(p.src + (long long)bd.img * p.C * plane);
+      // first layers: element offset of channel 0, channel stride and live-plane mask of this image
+      long long vbase = (long long)bd.img * p.cvalid * plane, vcstride = plane;
+      uint32_t vmask = 0xfu;
+      if (p.use_view) {
+        const long long rr = bd.img / p.view.T;
+        const int tt = bd.img - (int)rr * p.view.T;
+        vbase = rr * p.view.stride_r + (long long)tt * p.view.stride_t;
+        vcstride = p.view.stride_c;
+        if (p.view.pflag) {                         // planes older than a reset read as zero (a2c/utils.py:37-40)
+          const uint8_t* pf = p.view.pflag + rr * p.view.pflag_stride_r + tt;
+          vmask = 0;
+          bool live = true;
+          for (int c = p.view.fs - 1; c >= 0; --c) {
+            if (live) vmask |= 1u << c;
+            live = live && (pf[c] == 0);
+          }
+        }
+      }
       const float4* mimg = p.mask ? reinterpret_cast<const float4*>(p.mask + (long long)bd.img * p.C * plane) : nullptr;
       for (int cy = 0; cy < p.cs && !(p.dbg & 4); ++cy) {
         const int ntask = (bd.rows + p.rext_y[cy]) * p.ncg;    // (r, cg)
@@ -229,10 +252,33 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
           const int r = task / p.ncg, cg = task - r * p.ncg;
           const int sy = (bd.r0 + r) * p.cs + cy - p.p0y;
           const bool rowok = (unsigned)sy < (unsigned)p.SH;
-          const int e0 = (rowok ? (cg * 4 * plane + sy * p.SW) >> 2 : 0) + m;   // float4 index, channel 0
-          const int pl4 = rowok ? plane >> 2 : 0;
-          float4 v0 = __ldg(simg + e0), v1 = __ldg(simg + e0 + pl4), v2 = __ldg(simg + e0 + 2 * pl4),
-                 v3 = __ldg(simg + e0 + 3 * pl4);
+          float4 v0, v1, v2, v3;
+          int e0 = 0, pl4 = 0;
+          if (p.cvalid < p.C) {
+            // first layer: cvalid (<= 4) channels, f32 tensor or uint8 ring view; the second channel group is
+            // padding that stays zero from the initial clear
+            if (cg != 0) continue;
+            float4 vv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              vv[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (rowok && c < p.cvalid && ((vmask >> c) & 1u)) {
+                const long long a = vbase + c * vcstride + (long long)sy * p.SW + 4 * m;
+                if (p.use_view) {
+                  const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(p.view.base) + a));
+                  vv[c] = make_float4((float)(w & 0xff), (float)((w >> 8) & 0xff), (float)((w >> 16) & 0xff), (float)(w >> 24));
+                } else {
+                  vv[c] = __ldg(reinterpret_cast<const float4*>(p.src + a));
+                }
+              }
+            }
+            v0 = vv[0]; v1 = vv[1]; v2 = vv[2]; v3 = vv[3];
+          } else {
+          e0 = (rowok ? (cg * 4 * plane + sy * p.SW) >> 2 : 0) + m;   // float4 index, channel 0
+          pl4 = rowok ? plane >> 2 : 0;
+          v0 = __ldg(simg + e0); v1 = __ldg(simg + e0 + pl4); v2 = __ldg(simg + e0 + 2 * pl4);
+          v3 = __ldg(simg + e0 + 3 * pl4);
+          }
           if (mimg) {
             const float4 m0 = __ldg(mimg + e0), m1 = __ldg(mimg + e0 + pl4), m2 = __ldg(mimg + e0 + 2 * pl4),
                          m3 = __ldg(mimg + e0 + 3 * pl4);
@@ -306,8 +352,12 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
                 uint32_t a_hi = a_buf + p.taps[g].a_off16 + (uint32_t)(t * TM);
                 uint32_t b_hi = b_w0 + (uint32_t)(g * p.ksteps) * (WBLK >> 4);
                 for (int ks = 0; ks < p.ksteps; ++ks) {
-                  mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + half16, b_hi, acc);
-                  mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi, b_hi + wlo16, 1u);
+                  if (p.nsplit == 2) {
+                    mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + half16, b_hi, acc);
+                    mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi, b_hi + wlo16, 1u);
+                  } else {
+                    mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi, b_hi + wlo16, acc);
+                  }
                   mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi, b_hi, 1u);
                   acc = 1u;
                   a_hi += kstep16;
@@ -499,20 +549,30 @@ static int shift_run(ShiftParams& p, FillTaps fill, cudaStream_t st) {
 }
 
 // 0 = ran, 1 = not supported (caller falls back), else error
-int conv_fwd_shift_try(const float* X, const float* Wt, const float* bias, float* Y, int N,
-                       const a2c_conv_shape* s, int relu, cudaStream_t st) {
+int conv_fwd_shift_try(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias, float* Y,
+                       int N, const a2c_conv_shape* s, int relu, cudaStream_t st) {
   const int K = s->K, S = s->stride, P = s->pad;
-  if (!shift_enabled() || !X || K != 3 || P != 1 || (S != 1 && S != 2) || (s->Cin % 8) != 0) return 1;
+  // first layers (<= 4 channels, stride 1): channels padded to one 8-deep k-step; the source may be
+  // the uint8 plane ring, whose {0,1} values are exact in TF32 (no lo operand)
+  const bool first = s->Cin <= 4 && S == 1;
+  if (!shift_enabled() || (!X && !xview) || K != 3 || P != 1 || (S != 1 && S != 2)) return 1;
+  if (!first && ((s->Cin % 8) != 0 || xview)) return 1;
+  if (xview && (xview->dtype != 0 || xview->fs != s->Cin || (reinterpret_cast<uintptr_t>(xview->base) & 3) ||
+                ((xview->stride_r | xview->stride_t | xview->stride_c) & 3)))
+    return 1;
   if ((S == 2 && ((s->H | s->W) & 1)) || s->Cout > 128) return 1;
   static thread_local ShiftParams p;
   memset(&p, 0, sizeof(p));
-  p.src = X; p.N = N; p.C = s->Cin; p.SH = s->H; p.SW = s->W; p.ncg = s->Cin / 4; p.ksteps = s->Cin / 8;
+  const int Cp = first ? 8 : s->Cin;
+  p.src = xview ? nullptr : X; p.N = N; p.C = Cp; p.SH = s->H; p.SW = s->W; p.ncg = Cp / 4; p.ksteps = Cp / 8;
+  p.cvalid = s->Cin; p.nsplit = xview ? 1 : 2;
+  if (xview) { p.view = *xview; p.use_view = 1; }
   // source (y, x) lives in parity plane ((y+P) % S, (x+P) % S) at ((y+P) / S, (x+P) / S); tap
   // (ky, kx) of output (oy, ox) reads plane (ky % S, kx % S) at (oy + ky / S, ox + kx / S)
   p.cs = S; p.p0y = P; p.p0x = P;
   p.PW = s->OW + (K - 1) / S;
   for (int cy = 0; cy < S; ++cy) p.rext_y[cy] = (K - 1 - cy) / S;
-  if ((s->W & 3) || s->W > 128 || (reinterpret_cast<uintptr_t>(X) & 15)) return 1;
+  if ((s->W & 3) || s->W > 128 || (!xview && (reinterpret_cast<uintptr_t>(X) & 15))) return 1;
   p.QH = s->OH; p.noc = 1; p.os = 1;
   p.oc[0] = {0, K * K, 0, 0, s->OH, s->OW};
   p.ntaps_total = K * K; p.nch = K;                 // one accumulator chain per kernel row
@@ -544,6 +604,7 @@ int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, f
   memset(&p, 0, sizeof(p));
   p.src = dY; p.mask = Ymask; p.N = N; p.C = s->Cout; p.SH = s->OH; p.SW = s->OW;
   p.ncg = s->Cout / 4; p.ksteps = s->Cout / 8;
+  p.cvalid = s->Cout; p.nsplit = 2;
   p.cs = 1;
   // tap k contributes to dX row y = S*j + a from dY row j + d, d = (a + P - k) / S when divisible
   int dmin = 0, dmax = 0;

@@ -467,8 +467,8 @@ int conv_wgrad_tc_try(const float* X, const a2c_state_view* xview, const float* 
                       long long workspace_bytes, int precision, cudaStream_t st);
 
 // conv_shift_tc.cu (3xTF32 only): 3x3 pad-1 layers as shifted-descriptor GEMMs, no im2col
-int conv_fwd_shift_try(const float* X, const float* Wt, const float* bias, float* Y, int N,
-                       const a2c_conv_shape* s, int relu, cudaStream_t st);
+int conv_fwd_shift_try(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias, float* Y,
+                       int N, const a2c_conv_shape* s, int relu, cudaStream_t st);
 int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
                          const a2c_conv_shape* s, cudaStream_t st);
 
@@ -502,10 +502,14 @@ int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
   // First layers (Cin <= 4) run on the FFMA kernel: it is faster there (K = Cin*k*k is tiny, the
   // tensor-core tile would be mostly padding) and its fp32 rounding keeps the ReLU masks of the
   // {0,1}-valued input layer identical to the reference's.
+  if (precision == 1) {
+    A2C_ARG_CHECK(xview || X, "conv_fwd: null input");
+    int rc = conv_fwd_shift_try(X, xview, Wt, bias, Y, N, s, relu, as_stream(stream));
+    if (rc != 1) return rc;
+  }
   if (precision != 0 && s->Cin > 4) {
     A2C_ARG_CHECK(xview || X, "conv_fwd: null input");
-    int rc = (precision == 1 && !xview) ? conv_fwd_shift_try(X, Wt, bias, Y, N, s, relu, as_stream(stream)) : 1;
-    if (rc != 1) return rc;
+    int rc;
     rc = conv_fwd_patch_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
     if (rc != 1) return rc;
     rc = conv_fwd_tc_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
