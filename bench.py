@@ -271,7 +271,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (%.0f MB of frames per step)" % (R * T * FRAME_BYTES / 1e6),
                    "optim": hyps["optim_type"],
                    "arithmetic": {0: "fp32 FFMA kernels", 1: "fp32 results via the 3xTF32 split on tcgen05 "
-                                  "(fp32 accumulate, 1e-5 parity); first conv layer on fp32 FFMA",
+                                  "(fp32 accumulate, 1e-5 parity)",
                                   2: "single-pass TF32 on tcgen05 (2e-3)"}[args.precision]},
         "e2e": {"value": e2e_value, "unit": "transitions/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 20,

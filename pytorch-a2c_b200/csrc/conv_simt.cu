@@ -499,9 +499,8 @@ int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
   if (int rc = check_shape(s)) return rc;
   A2C_ARG_CHECK(Wt && Y && N >= 0, "conv_fwd: bad args");
   if (N == 0) return 0;
-  // First layers (Cin <= 4) run on the FFMA kernel: it is faster there (K = Cin*k*k is tiny, the
-  // tensor-core tile would be mostly padding) and its fp32 rounding keeps the ReLU masks of the
-  // {0,1}-valued input layer identical to the reference's.
+  // 3x3 pad-1 layers (first layers included: they read the uint8 ring directly) run as shift-GEMMs;
+  // the other tensor-core paths take layers with more than 4 input channels, the rest is FFMA.
   if (precision == 1) {
     A2C_ARG_CHECK(xview || X, "conv_fwd: null input");
     int rc = conv_fwd_shift_try(X, xview, Wt, bias, Y, N, s, relu, as_stream(stream));
@@ -588,9 +587,8 @@ int a2c_conv2d_bwd_weight(const float* X, const a2c_state_view* xview, const flo
     if (dbias) A2C_CUDA_CHECK(cudaMemsetAsync(dbias, 0, sizeof(float) * s->Cout, st));
     return 0;
   }
-  // First layers (Cin <= 4, {0,1} inputs, gradients that are sums of ~1e7 cancelling terms) stay on
-  // the FFMA kernel: it is faster there (few taps) and its round-to-nearest partial sums keep the
-  // result as accurate as the fp32 reference; the TMEM accumulator truncates.
+  // 3x3 pad-1 layers run as shift-GEMMs (short TMEM chains, fp32 running sums, double reduction);
+  // the older tensor-core paths take the remaining layers with more than 4 input channels.
   if (precision == 1) {
     int rc = conv_wgrad_shift_try(X, xview, dY, Ymask, dW, dbias, N, s, workspace, workspace_bytes, st);
     if (rc != 1) return rc;
