@@ -56,3 +56,25 @@ def test_no_cpu_fallback():
     net = models.FCModel([2, 80, 80], 3, h_size=8)
     with pytest.raises(_lib.A2CError):
         net(torch.zeros(1, 2, 80, 80))
+
+
+def test_fused_mask_query_is_host_logic():
+    """a2c_conv2d_fused_mask tells the caller which backward entries apply the ReLU mask
+    themselves (bit 0 data, bit 1 weight); pure host logic, so it runs without a GPU."""
+    from a2c_b200 import _lib
+    lib = _lib.load()
+
+    def shape(cin, cout, h, k, s, p):
+        oh = (h - k + 2 * p) // s + 1
+        return _lib.ConvShape(cin, cout, h, h, oh, oh, k, s, p)
+
+    def q(sh, prec, view=0):
+        return lib.a2c_conv2d_fused_mask(ctypes.byref(sh), prec, view)
+
+    assert q(shape(16, 24, 80, 3, 1, 1), 0) == 3            # FFMA kernels always take the mask
+    assert q(shape(16, 24, 80, 3, 1, 1), 1) == 3            # ConvModel layers 2-4: shift-GEMM both ways
+    assert q(shape(24, 32, 80, 3, 2, 1), 1) == 3
+    assert q(shape(32, 64, 40, 3, 2, 1), 1) == 3
+    assert q(shape(2, 16, 80, 3, 1, 1), 1, view=1) & 2      # first layer from the uint8 ring
+    assert q(shape(16, 32, 19, 4, 2, 0), 1) == 0            # A3C's 4x4 s2 layer: pre-masked gradient
+    assert q(shape(16, 24, 80, 3, 1, 1), 2) == 0            # single-pass TF32 paths want the masked dY
