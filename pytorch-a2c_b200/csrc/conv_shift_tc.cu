@@ -137,7 +137,9 @@ __device__ __forceinline__ void store_split(uint8_t* dst, int half_bytes, float 
   *reinterpret_cast<float4*>(dst + half_bytes) = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);
 }
 
-template <int NPAD>
+// FIRST: first-layer variant (<= 4 real channels padded to one k-step, optional uint8 ring source,
+// optional 2-product split); a template flag so the general kernel's hot loops stay branch-free.
+template <int NPAD, bool FIRST>
 __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_constant__ ShiftParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int NCOL = NPAD / 2;                      // accumulator columns per drain warp
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
           const bool rowok = (unsigned)sy < (unsigned)p.SH;
           float4 v0, v1, v2, v3;
           int e0 = 0, pl4 = 0;
-          if (p.cvalid < p.C) {
+          if constexpr (FIRST) {
             // first layer: cvalid (<= 4) channels, f32 tensor or uint8 ring view; the second channel group is
             // padding that stays zero from the initial clear
             if (cg != 0) continue;
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
                 uint32_t a_hi = a_buf + p.taps[g].a_off16 + (uint32_t)(t * TM);
                 uint32_t b_hi = b_w0 + (uint32_t)(g * p.ksteps) * (WBLK >> 4);
                 for (int ks = 0; ks < p.ksteps; ++ks) {
-                  if (p.nsplit == 2) {
+                  if (!FIRST || p.nsplit == 2) {
                     mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + half16, b_hi, acc);
                     mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi, b_hi + wlo16, 1u);
                   } else {
@@ -496,9 +498,9 @@ static bool shift_plan(ShiftParams* p, int npad) {
   return false;
 }
 
-template <int NPAD>
+template <int NPAD, bool FIRST = false>
 static int shift_launch(ShiftParams& p, cudaStream_t st) {
-  auto kern = conv_shift_kernel<NPAD>;
+  auto kern = conv_shift_kernel<NPAD, FIRST>;
   static bool configured = false;
   if (!configured) {
     A2C_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_LIMIT));
@@ -539,8 +541,14 @@ static int shift_run(ShiftParams& p, FillTaps fill, cudaStream_t st) {
     { const char* e = getenv("A2C_SHIFT_DBG"); p.dbg = e ? atoi(e) : 0; }
     for (int n0 = 0; n0 < p.J; n0 += npad) {
       p.n0 = n0;
-      int rc = npad == 64 ? tc::shift_launch<64>(p, st) : npad == 32 ? tc::shift_launch<32>(p, st)
-                                                                     : tc::shift_launch<16>(p, st);
+      int rc;
+      if (p.cvalid < p.C) {
+        if (npad == 64) return 1;                                 // first layers: 16 / 32 wide only
+        rc = npad == 32 ? tc::shift_launch<32, true>(p, st) : tc::shift_launch<16, true>(p, st);
+      } else {
+        rc = npad == 64 ? tc::shift_launch<64>(p, st) : npad == 32 ? tc::shift_launch<32>(p, st)
+                                                                   : tc::shift_launch<16>(p, st);
+      }
       if (rc) return rc;
     }
     return 0;
