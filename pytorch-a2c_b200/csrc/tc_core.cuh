@@ -67,21 +67,6 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
       : "memory");
 }
 
-// Same instruction with the descriptors given as 32-bit halves: only the low word (start
-// address, LBO) changes inside a kernel, so issue loops can do 32-bit (uniform-register)
-// arithmetic on it and leave the constant high word (SBO, version, swizzle) alone.
-__device__ __forceinline__ void mma_tf32_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                           uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
-      ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 // Variant for issue-bound loops: the instruction descriptor and the constant high descriptor
 // word are immediates (ptxas keeps them in uniform registers instead of re-materialising them
 // through R2UR for every instruction); only the low descriptor words are register operands.
