@@ -359,49 +359,48 @@ __global__ void __launch_bounds__(P_THREADS, 1) conv_patch_fwd_kernel(const __gr
       }
     }
   } else if (warp == P_MMA) {
-    // One lane runs the whole issue loop; descriptors are advanced by integer adds on the
-    // 14-bit (address >> 4) field, stage / chunk indices by counters (no div / mod).
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
-      const uint64_t a_desc0 = make_desc(smem_u32(sm.stages));
-      const uint64_t b_res0 = make_desc(smem_u32(sm.bres));
-      const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
-      StageRing ring(p.stages);
-      int chunk = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int inchunk = 0;
-        for (int i = 0; i < p.nkb; ++i, ring.next()) {
-          const int buf = chunk & 1;
-          if (inchunk == 0) {
-            mbar_wait(&sm.acc_empty[buf], ((chunk >> 1) & 1) ^ 1);
-            tc_fence_after();
-          }
-          mbar_wait(&sm.full[ring.s], ring.par);
+    // convergent warp, one elected lane, descriptor low words in uniform registers (mma_tf32_imm)
+    constexpr uint32_t idesc = make_idesc(BN);
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
+    const uint32_t a_w0 = ((smem_u32(sm.stages) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_res0 = ((smem_u32(sm.bres) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
+    StageRing ring(p.stages);
+    int chunk = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int inchunk = 0;
+      for (int i = 0; i < p.nkb; ++i, ring.next()) {
+        const int buf = chunk & 1;
+        if (inchunk == 0) {
+          mbar_wait(&sm.acc_empty[buf], ((chunk >> 1) & 1) ^ 1);
           tc_fence_after();
-          const uint32_t tmem_d = tmem_base + buf * BN;
-          const uint64_t a_hi = a_desc0 + (uint64_t)(ring.s * stage_step);
-          const uint64_t a_lo = a_hi + (A_BYTES >> 4);
-          const uint64_t b_hi = p.b_resident ? b_res0 + (uint64_t)(i * (BPAIR >> 4)) : a_hi + (APAIR >> 4);
-          const uint64_t b_lo = b_hi + (B_BYTES >> 4);
+        }
+        mbar_wait(&sm.full[ring.s], ring.par);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        const uint32_t a_hi = a_w0 + ring.s * stage_step;
+        const uint32_t a_lo = a_hi + (A_BYTES >> 4);
+        const uint32_t b_hi = p.b_resident ? b_res0 + (uint32_t)i * (BPAIR >> 4) : a_hi + (APAIR >> 4);
+        const uint32_t b_lo = b_hi + (B_BYTES >> 4);
+        const bool last = (inchunk + 1 == KC) || (i == p.nkb - 1);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < KB / 8; ++kk) {
-            const uint64_t ko = kk * 2;      // 32 bytes per UMMA_K step
+            const uint32_t ko = kk * 2;      // 32 bytes per UMMA_K step
             const uint32_t first = (inchunk | kk) ? 1u : 0u;
             if constexpr (SPLIT3) {
-              mma_tf32(tmem_d, a_lo + ko, b_hi + ko, idesc, first);
-              mma_tf32(tmem_d, a_hi + ko, b_lo + ko, idesc, 1u);
-              mma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, 1u);
+              mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_lo + ko, b_hi + ko, first);
+              mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + ko, b_lo + ko, 1u);
+              mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + ko, b_hi + ko, 1u);
             } else {
-              mma_tf32(tmem_d, a_hi + ko, b_hi + ko, idesc, first);
+              mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + ko, b_hi + ko, first);
             }
           }
           mma_commit(&sm.empty[ring.s]);
-          if (++inchunk == KC || i == p.nkb - 1) {
-            mma_commit(&sm.acc_full[buf]);
-            inchunk = 0;
-            ++chunk;
-          }
+          if (last) mma_commit(&sm.acc_full[buf]);
         }
+        __syncwarp();
+        if (last) { inchunk = 0; ++chunk; } else ++inchunk;
       }
     }
   } else if (warp >= P_DRAIN0 && warp < P_DRAIN0 + NUM_EPI_WARPS) {
