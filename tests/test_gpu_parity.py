@@ -409,29 +409,43 @@ def test_layernorm(dev):
 
 
 def test_gru_cell(dev):
+    """GRU cell forward / backward against the oracle.  The float64 evaluation of the same formulas
+    is the yardstick: the device must be within TOL of it; against the fp32 CPU oracle the allowance
+    grows by that oracle's own distance from float64 (its matmul rounding depends on the host CPU:
+    one box in six showed 1.7e-5 on the last row)."""
     ops = ops_mod()
     gen = torch.Generator().manual_seed(2)
     B, Hd = 37, 64
-    p = {"gru.W_x": torch.randn(3, Hd, Hd, generator=gen) / 8,
-         "gru.W_h": torch.randn(3, Hd, Hd, generator=gen) / 8,
-         "gru.b": torch.randn(3, 1, Hd, generator=gen)}
-    p = {k: v.requires_grad_(True) for k, v in p.items()}
-    x = torch.randn(B, Hd, generator=gen).requires_grad_(True)
-    h = torch.randn(B, Hd, generator=gen).requires_grad_(True)
+    p0 = {"gru.W_x": torch.randn(3, Hd, Hd, generator=gen) / 8,
+          "gru.W_h": torch.randn(3, Hd, Hd, generator=gen) / 8,
+          "gru.b": torch.randn(3, 1, Hd, generator=gen)}
+    x0 = torch.randn(B, Hd, generator=gen)
+    h0 = torch.randn(B, Hd, generator=gen)
     keep = (torch.rand(B, generator=gen) < 0.7).float()
-    hn = O.gru_cell(p, x, h)
     g1, g2 = torch.randn(B, Hd, generator=gen), torch.randn(B, Hd, generator=gen)
-    (hn * g1 + hn * keep[:, None] * g2).sum().backward()
-    d = {k: v.detach().to(dev).requires_grad_(True) for k, v in p.items()}
-    xd, hd = x.detach().to(dev).requires_grad_(True), h.detach().to(dev).requires_grad_(True)
+
+    def cpu_eval(dtype):
+        p = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in p0.items()}
+        x = x0.detach().clone().to(dtype).requires_grad_(True)
+        h = h0.detach().clone().to(dtype).requires_grad_(True)
+        hn = O.gru_cell(p, x, h)
+        (hn * g1.to(dtype) + hn * keep.to(dtype)[:, None] * g2.to(dtype)).sum().backward()
+        out = {"hnew": hn.detach(), "hnext": (hn * keep.to(dtype)[:, None]).detach(), "x": x.grad, "h": h.grad}
+        out.update({k: v.grad for k, v in p.items()})
+        return {k: v.double().numpy() for k, v in out.items()}
+
+    ref32, ref64 = cpu_eval(torch.float32), cpu_eval(torch.float64)
+    d = {k: v.detach().clone().to(dev).requires_grad_(True) for k, v in p0.items()}
+    xd, hd = x0.detach().clone().to(dev).requires_grad_(True), h0.detach().clone().to(dev).requires_grad_(True)
     hnew, hnext = ops.GRUCellFn.apply(xd, hd, d["gru.W_x"], d["gru.W_h"], d["gru.b"], keep.to(dev))
-    assert H.rel_err(hnew.detach().cpu().numpy(), hn.detach().numpy()) < TOL
-    assert H.rel_err(hnext.detach().cpu().numpy(), (hn * keep[:, None]).detach().numpy()) < TOL
     (hnew * g1.to(dev) + hnext * g2.to(dev)).sum().backward()
-    assert H.rel_err(xd.grad.cpu().numpy(), x.grad.numpy()) < TOL
-    assert H.rel_err(hd.grad.cpu().numpy(), h.grad.numpy()) < TOL
-    for k in p:
-        assert H.rel_err(d[k].grad.cpu().numpy(), p[k].grad.numpy()) < TOL, k
+    got = {"hnew": hnew.detach(), "hnext": hnext.detach(), "x": xd.grad, "h": hd.grad}
+    got.update({k: v.grad for k, v in d.items()})
+    for k, v in got.items():
+        v = v.cpu().double().numpy()
+        e_ref = H.rel_err(ref32[k], ref64[k])
+        assert H.rel_err(v, ref64[k]) < TOL, (k, "device vs float64", H.rel_err(v, ref64[k]), "fp32 oracle vs float64", e_ref)
+        assert H.rel_err(v, ref32[k]) < TOL + e_ref, (k, "device vs fp32 oracle", H.rel_err(v, ref32[k]), e_ref)
 
 
 # ------------------------------------------------ models / Updater / Runner ----
