@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define A2C_ERR_ARG (-1)
-#define A2C_ABI_VERSION 1
+#define A2C_ABI_VERSION 2
 
 int a2c_abi_version(void);
 const char* a2c_last_error(void);
@@ -49,15 +49,35 @@ long long a2c_launch_count(void);
  * ---------------------------------------------------------------------- */
 
 /* frames u8 [R, F, 210,160,3], reset u8 [R, F] -> planes[r, j0+f], pflag[r, j0+f]
- * for f < F.  `variant`: 0 = TMA-staged (default), 1 = direct 128-bit loads. */
+ * for f < F.  `variant`: 0 = TMA-staged, 2-deep rings, two CTAs per SM (default); 1 = direct
+ * 128-bit loads; 2 = TMA-staged, 4-deep ring, one CTA per SM. */
 int a2c_obs_prep_stack(const uint8_t* frames, const uint8_t* reset, uint8_t* planes,
                        uint8_t* pflag, int R, int F, int P, int j0, int variant, void* stream);
 
-/* Same, frames/reset in (pinned) HOST memory; copies through an internal device
- * staging buffer in chunks and synchronises the stream before returning. */
+/* Same, frames/reset in pinned (page-locked, mapped) HOST memory.  Zero-copy: the stage-1
+ * TMA boxes are fetched straight from host memory, so only the 80 selected rows of each frame
+ * (38 % of its bytes) cross PCIe.  Synchronises `stream` before returning (the caller may
+ * reuse the host buffers immediately): the per-step acting path. */
 int a2c_obs_prep_stack_host(const uint8_t* frames_host, const uint8_t* reset_host,
                             uint8_t* planes, uint8_t* pflag, int R, int F, int P, int j0,
                             void* stream);
+
+/* Pipelined host ingest for whole rollouts (the update path): ONE asynchronous copy per
+ * rollout on a copy stream, overlapped with compute, then stage 1 from the device staging
+ * buffer.  `layout` selects what crosses PCIe and how the staging buffer is laid out:
+ *   0: the 80 selected rows (35, 37, ..., 193) of each frame, u8 [n, 80, 480]: 38,400 B per
+ *      frame, one cudaMemcpy3DAsync with 480-byte rows;
+ *   1: the cropped band (rows 35..193) of each frame, u8 [n, 159, 480]: 76,320 contiguous
+ *      bytes per frame, one cudaMemcpy2DAsync;
+ *   2: whole frames, u8 [n, 210, 160, 3]: one contiguous cudaMemcpyAsync.
+ * a2c_obs_ingest_rows_async does not synchronise: the pinned host buffer must stay untouched
+ * until the caller's event on `stream` completes.  a2c_obs_prep_stack_rows is
+ * a2c_obs_prep_stack reading the staging layout. */
+long long a2c_obs_ingest_bytes_per_frame(int layout);
+int a2c_obs_ingest_rows_async(const uint8_t* frames_host, uint8_t* rows, long long n_frames,
+                              int layout, void* stream);
+int a2c_obs_prep_stack_rows(const uint8_t* rows, const uint8_t* reset, uint8_t* planes,
+                            uint8_t* pflag, int R, int F, int P, int j0, int layout, void* stream);
 
 /* Moves the last `fs` planes (+flags) of every slot to the head of its ring:
  * the bookmark state of a2c/runner.py:246. */
@@ -109,6 +129,14 @@ int a2c_delta_scan(float* rewards, float* dones, const float* values, float* del
 int a2c_discount(const float* array, const float* dones, float* out, double* stats,
                  long long N, float factor, void* stream);
 
+/* Both scans of Updater.update_model in one launch (a2c/updater.py:70-71: advs =
+ * discount(deltas, dones, gamma*lambda); :86-88: returns = discount(rewards, dones,
+ * gamma)), bit-exact.  rewards / returns may both be NULL (use_nstep_rets).
+ * stats f64 [4] (may be NULL) gets sum(adv), sum(adv^2), sum(ret), sum(ret^2) added. */
+int a2c_discount2(const float* deltas, const float* rewards, const float* dones, float* advs,
+                  float* returns, double* stats, long long N, float gamma_lambda, float gamma,
+                  void* stream);
+
 /* ------------------------------------------------------------------------
  * Stage 3 -- fused A2C loss forward + backward (discrete actions)
  * replaces a2c/updater.py:97-106,119-127 and the autograd of those lines.
@@ -150,10 +178,21 @@ int a2c_gemm(const float* A, long long sam, long long sak, const float* B, long 
              int relu, int beta, int precision, void* workspace, long long workspace_bytes,
              void* stream);
 
+/* a2c_gemm whose result is gated by a ReLU mask laid out like C: C = Cmask > 0 ? value : 0.
+ * Used for the input gradient of a Linear layer that reads a ReLU output (ConvModel /
+ * GRUModel `resize_emb` on the conv features, a2c/models.py:247,626): the mask of the last conv
+ * layer is applied where its output gradient is produced. */
+int a2c_gemm_masked(const float* A, long long sam, long long sak, const float* B, long long sbk,
+                    long long sbn, float* C, long long ldc, const float* bias, const float* Cmask,
+                    int M, int N, int K, int relu, int beta, int precision, void* workspace,
+                    long long workspace_bytes, void* stream);
+
 /* First-layer linear on a state view: Y[n, :] = relu?(flatten(state_n) * W^T + b).
- * W f32 [Nout, fs*6400]. */
+ * W f32 [Nout, fs*6400].  `workspace` (may be NULL) enables split-K when the output has
+ * fewer tiles than the GPU has SMs (C1: 60 x 256). */
 int a2c_linear_state_fwd(const a2c_state_view* x, const float* W, const float* bias, float* Y,
-                         int R, int Nout, int relu, void* stream);
+                         int R, int Nout, int relu, void* workspace, long long workspace_bytes,
+                         void* stream);
 /* dW[Nout, fs*6400] = dY^T * flatten(states). */
 int a2c_linear_state_wgrad(const a2c_state_view* x, const float* dY, float* dW, int R, int Nout,
                            void* workspace, long long workspace_bytes, void* stream);
@@ -180,6 +219,19 @@ int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
  * output whose ReLU gates dY. */
 int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
                         const a2c_conv_shape* s, int precision, void* stream);
+/* "Mask at the source" form used by a stack of Conv+ReLU layers (a2c/models.py:312,685): dY is
+ * ALREADY masked by this layer's ReLU; X is this layer's input, i.e. the previous layer's ReLU
+ * output.  dX = conv2d_transpose(dY) * (X > 0) is the previous layer's masked output gradient, and
+ * dbias_prev f32 [Cin] (may be NULL) its bias gradient (per-channel sums of dX), both produced in
+ * the epilogue of the input-gradient kernel: no backward kernel re-reads a forward output as a
+ * mask and no separate bias-sum pass over dY exists.  workspace: >= 8*Cin bytes when dbias_prev. */
+int a2c_conv2d_bwd_data_relu(const float* dY, const float* Wt, const float* X, float* dX,
+                             float* dbias_prev, int N, const a2c_conv_shape* s, int precision,
+                             void* workspace, long long workspace_bytes, void* stream);
+/* out f32 [C] = per-channel sums of X f32 [N, C, HW] where mask > 0 (mask may be NULL): the bias
+ * gradient of the last conv layer from its masked output gradient.  workspace >= 8*C bytes. */
+int a2c_channel_sum(const float* X, const float* mask, float* out, int N, int C, int HW,
+                    void* workspace, long long workspace_bytes, void* stream);
 /* Which backward entries apply the ReLU mask (Ymask > 0) themselves on the path they take for
  * this shape / precision: bit 0 = a2c_conv2d_bwd_data, bit 1 = a2c_conv2d_bwd_weight.  A caller
  * holding an unmasked dY passes Ymask to those and pre-masks dY (a2c_relu_bwd) for the others;

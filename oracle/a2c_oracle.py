@@ -283,7 +283,7 @@ def a2c_loss(logits, vals, actions, advs, returns, hyps):
     no gradient.  Negative actions index from the end, as torch indexing does
     for the reference's ``log_softs[arange, actions]``."""
     lsm = F.log_softmax(logits, dim=-1)
-    idx = torch.arange(len(actions))
+    idx = torch.arange(len(actions), device=logits.device)
     log_ps = lsm[idx, actions]
     entr_loss = -hyps["entr_coef"] * (lsm * F.softmax(logits, dim=-1)).sum(-1).mean()
     pi_loss = hyps["pi_coef"] * -(log_ps * advs).mean()
@@ -296,13 +296,17 @@ class UpdaterOracle:
     """a2c/updater.py:9-137.  ``compute`` is update_model up to and including
     loss.backward() + clip_grad_norm_; ``step`` adds optimizer.step()."""
 
-    def __init__(self, model, params, hyps, dtype=torch.float32):
+    def __init__(self, model, params, hyps, dtype=torch.float32, device="cpu"):
         # dtype=float64 evaluates the same algorithm in double (scans stay fp32,
-        # they are bit-exact by construction): the yardstick for ill-conditioned sums
+        # they are bit-exact by construction): the yardstick for ill-conditioned sums.
+        # device="cuda" (tests only, with float64) runs the SAME torch ops on the GPU's fp64
+        # units so that full-size gradients can be compared tensor by tensor in seconds; its
+        # output is pinned to the committed CPU-generated fp64 fixtures before it is trusted.
         self.model = model
         self.hyps = hyps
         self.dtype = dtype
-        self.p = OrderedDict((k, torch.as_tensor(v).to(dtype).clone()
+        self.device = torch.device(device)
+        self.p = OrderedDict((k, torch.as_tensor(v).to(self.device, dtype).clone()
                               .requires_grad_(True)) for k, v in params.items())
         self.optim = getattr(torch.optim, hyps["optim_type"])(
             list(self.p.values()), lr=hyps["lr"])            # :226-229
@@ -311,11 +315,11 @@ class UpdaterOracle:
 
     def forward(self, shared):
         hyps = self.hyps
-        states = shared["states"].to(self.dtype)
+        states = shared["states"].to(self.device, self.dtype)
         if is_recurrent(self.model):
-            hs = shared["h_states"].to(self.dtype)
+            hs = shared["h_states"].to(self.device, self.dtype)
             if hyps["use_bptt"]:                             # :76
-                return bptt(self.model, self.p, states, hs, shared["dones"].to(self.dtype),
+                return bptt(self.model, self.p, states, hs, shared["dones"].to(self.device, self.dtype),
                             hyps["n_rollouts"], hyps["n_tsteps"])
             v, l, _ = model_forward(self.model, self.p, states, hs)  # :78
             return v, l
@@ -323,13 +327,14 @@ class UpdaterOracle:
 
     def compute(self, shared):
         hyps = self.hyps
-        dones = shared["dones"].reshape(-1)
-        advs = discount(shared["deltas"], dones, hyps["gamma"] * hyps["lambda_"]).to(self.dtype)  # :70
+        dones = shared["dones"].reshape(-1).cpu()
+        advs = discount(shared["deltas"].cpu(), dones,
+                        hyps["gamma"] * hyps["lambda_"]).to(self.device, self.dtype)  # :70
         vals, logits = self.forward(shared)
         if hyps["use_nstep_rets"]:                           # :83-84
             returns = advs + vals.detach().reshape(-1)
         else:                                                # :86-88
-            returns = discount(shared["rewards"], dones, hyps["gamma"]).to(self.dtype)
+            returns = discount(shared["rewards"].cpu(), dones, hyps["gamma"]).to(self.device, self.dtype)
         raw_advs, raw_returns = advs.clone(), returns.clone()
         if hyps.get("norm_returns", False):                  # :89-96
             if self.ret_mean is None:
@@ -341,7 +346,7 @@ class UpdaterOracle:
         if hyps["norm_advs"]:                                # :97-98 (unbiased std)
             advs = (advs - advs.mean()) / (advs.std() + 1e-6)
         loss, pi_loss, val_loss, entr_loss = a2c_loss(
-            logits, vals, shared["actions"].reshape(-1).long(), advs, returns, hyps)
+            logits, vals, shared["actions"].reshape(-1).long().to(self.device), advs, returns, hyps)
         for q in self.p.values():
             q.grad = None
         loss.backward()                                      # :128

@@ -51,19 +51,26 @@ SIGNATURES = {
     "a2c_launch_count": [],
     "a2c_obs_prep_stack": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "a2c_obs_prep_stack_host": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "a2c_obs_ingest_bytes_per_frame": [_i],
+    "a2c_obs_ingest_rows_async": [_p, _p, _ll, _i, _p],
+    "a2c_obs_prep_stack_rows": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "a2c_ring_carry": [_p, _p, _i, _i, _i, _p],
     "a2c_states_materialize": [_SV, _p, _i, _i, _p],
     "a2c_sample_action": [_p, _p, _p, _i, _i, _i, _p],
     "a2c_delta_scan": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _f, _p],
     "a2c_discount": [_p, _p, _p, _p, _ll, _f, _p],
+    "a2c_discount2": [_p, _p, _p, _p, _p, _p, _ll, _f, _f, _p],
     "a2c_loss_fwd_bwd": [_p, _p, _p, _p, _p, _p, _p, C.POINTER(LossCfg), _p, _p, _p, _ll, _i, _p],
     "a2c_gemm": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
-    "a2c_linear_state_fwd": [_SV, _p, _p, _p, _i, _i, _i, _p],
+    "a2c_gemm_masked": [_p, _ll, _ll, _p, _ll, _ll, _p, _ll, _p, _p, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
+    "a2c_linear_state_fwd": [_SV, _p, _p, _p, _i, _i, _i, _p, _ll, _p],
     "a2c_linear_state_wgrad": [_SV, _p, _p, _i, _i, _p, _ll, _p],
     "a2c_colsum": [_p, _p, _ll, _i, _p],
     "a2c_relu_bwd": [_p, _p, _p, _ll, _p],
     "a2c_conv2d_fwd": [_p, _SV, _p, _p, _p, _i, _CS, _i, _i, _p],
     "a2c_conv2d_bwd_data": [_p, _p, _p, _p, _i, _CS, _i, _p],
+    "a2c_conv2d_bwd_data_relu": [_p, _p, _p, _p, _p, _i, _CS, _i, _p, _ll, _p],
+    "a2c_channel_sum": [_p, _p, _p, _i, _i, _i, _p, _ll, _p],
     "a2c_conv2d_fused_mask": [_CS, _i, _i],
     "a2c_conv2d_bwd_weight_workspace": [_CS],
     "a2c_conv2d_bwd_weight": [_p, _SV, _p, _p, _p, _p, _i, _CS, _p, _ll, _i, _p],
@@ -77,8 +84,9 @@ SIGNATURES = {
     "a2c_clip_optim_step": [_p, _p, _p, _p, _p, C.POINTER(OptimCfg), _p, _ll, _p],
 }
 _RESTYPES = {"a2c_last_error": C.c_char_p, "a2c_launch_count": C.c_longlong,
+             "a2c_obs_ingest_bytes_per_frame": C.c_longlong,
              "a2c_conv2d_bwd_weight_workspace": C.c_longlong}
-_NO_STATUS = {"a2c_abi_version", "a2c_last_error", "a2c_launch_count",
+_NO_STATUS = {"a2c_abi_version", "a2c_last_error", "a2c_launch_count", "a2c_obs_ingest_bytes_per_frame",
               "a2c_conv2d_bwd_weight_workspace", "a2c_conv2d_fused_mask"}
 
 _lib = None

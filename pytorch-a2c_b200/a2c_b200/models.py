@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import Conv2dFn, GRUCellFn, LayerNormFn, LinearFn, LinearStateFn, View
+from .ops import ConvStackFn, GRUCellFn, GRUSequenceFn, LayerNormFn, LinearFn, LinearStateFn, View
 
 
 def _as_view(x):
@@ -37,8 +37,8 @@ def _check(bnorm, is_discrete):
         raise NotImplementedError("continuous actions are out of scope (Pong is discrete)")
 
 
-def _linear(x, lin, relu=False):
-    return LinearFn.apply(x, lin.weight, lin.bias, relu)
+def _linear(x, lin, relu=False, x_relu=False):
+    return LinearFn.apply(x, lin.weight, lin.bias, relu, x_relu)
 
 
 class _PolicyBase(nn.Module):
@@ -47,16 +47,35 @@ class _PolicyBase(nn.Module):
         for p in self.parameters():
             p.requires_grad = calc_bool
 
+    def activation_bytes_per_state(self):
+        """Rough device bytes one state keeps alive through forward + backward (fp32 layer
+        outputs, and about as much again for the gradients in flight); sizes the Updater's
+        micro-batches.  ConvModel: 4 x 332,800 x 2.6 = 3.4 MB."""
+        floats, size = 0, 80
+        for blk in getattr(self, "convs", []):
+            conv = blk[0]
+            size = (size - conv.kernel_size[0] + 2 * conv.padding[0]) // conv.stride[0] + 1
+            floats += conv.out_channels * size * size
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                floats += m.out_features
+        floats += 8 * getattr(self, "h_size", 0) if getattr(self, "is_recurrent", False) else 0
+        return int(4 * 2.6 * floats) + 4096
+
     @staticmethod
     def _conv_block(cin, cout, ksize, stride, padding):
         # Sequential(Conv2d, ReLU): index 0 carries the parameters ("convs.i.0.weight")
         return nn.Sequential(nn.Conv2d(cin, cout, ksize, stride=stride, padding=padding), nn.ReLU())
 
     def _features(self, view):
-        x = view
+        """Conv + ReLU stack as one autograd node; the Linear layer that consumes the flattened
+        features applies the last ReLU's mask in its input-gradient GEMM (``x_relu=True`` at the
+        call sites below), hence ``premasked=True``."""
+        geom = tuple((blk[0].stride[0], blk[0].padding[0]) for blk in self.convs)
+        params = []
         for blk in self.convs:
-            conv = blk[0]
-            x = Conv2dFn.apply(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0], True)
+            params += [blk[0].weight, blk[0].bias]
+        x = ConvStackFn.apply(view, True, geom, *params)
         return x.reshape(x.shape[0], -1)
 
 
@@ -119,7 +138,7 @@ class A3CModel(_PolicyBase):
         self.value = nn.Linear(h_size, 1)
 
     def encoder(self, state):
-        return _linear(self._features(_as_view(state)), self.proj_matrx)
+        return _linear(self._features(_as_view(state)), self.proj_matrx, x_relu=True)
 
     def policy(self, state_emb, bnorm=False):
         if bnorm:
@@ -157,7 +176,7 @@ class ConvModel(_PolicyBase):
         self.value = nn.Sequential(nn.Linear(conv_h, h_size), nn.ReLU(), nn.Linear(h_size, 1))
 
     def emb_net(self, state):
-        return _linear(self._features(_as_view(state)), self.resize_emb[0], relu=True)
+        return _linear(self._features(_as_view(state)), self.resize_emb[0], relu=True, x_relu=True)
 
     def policy(self, state_emb):
         pi = _linear(_linear(state_emb, self.pi[0], relu=True), self.pi[2])
@@ -214,7 +233,7 @@ class GRUModel(_PolicyBase):
         self.value = nn.Linear(h_size, 1)
 
     def emb_net(self, mdp_state):
-        return _linear(self._features(_as_view(mdp_state)), self.resize_emb[0], relu=True)
+        return _linear(self._features(_as_view(mdp_state)), self.resize_emb[0], relu=True, x_relu=True)
 
     def policy(self, h):
         return _linear(h, self.value), _linear(h, self.pi)
@@ -233,13 +252,8 @@ class GRUModel(_PolicyBase):
         emb = self.emb_net(states)                                  # (N, H), n = r*T + t
         emb_t = emb.view(R, T, H).transpose(0, 1).contiguous()      # time-major
         keep = (1.0 - dones.view(R, T)).t().contiguous()            # (T, R)
-        hs = h0.contiguous()
-        outs = []
-        for t in range(T):
-            hnew, hs = GRUCellFn.apply(emb_t[t], hs, self.gru.W_x, self.gru.W_h, self.gru.b,
-                                       keep[t])
-            outs.append(hnew)
-        hall = torch.stack(outs, 0).view(T * R, H)
+        hall = GRUSequenceFn.apply(emb_t, h0.contiguous(), self.gru.W_x, self.gru.W_h, self.gru.b,
+                                   keep).view(T * R, H)
         val, pi = self.policy(hall)
         A = pi.shape[-1]
         vals = val.view(T, R).t().reshape(-1)

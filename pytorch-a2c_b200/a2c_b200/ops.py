@@ -16,14 +16,19 @@ PLANE = 6400
 # GEMM / conv contraction mode: 0 = fp32 FFMA, 1 = 3xTF32 on tcgen05 (fp32 parity, the
 # default), 2 = single-pass TF32 on tcgen05 (stated tolerance 2e-3).  A2C_PRECISION overrides.
 import os as _os
-_PRECISION = int(_os.environ.get("A2C_PRECISION", "1"))
+_PRECISION = 1
 
 
 def set_precision(p):
     global _PRECISION
+    p = int(p)
     if p not in (0, 1, 2):
-        raise ValueError("precision must be 0 (fp32), 1 (3xTF32) or 2 (bf16)")
+        raise ValueError("precision must be 0 (fp32 FFMA), 1 (3xTF32 on tcgen05, fp32 parity) or "
+                         "2 (single-pass TF32 on tcgen05); got %r" % (p,))
     _PRECISION = p
+
+
+set_precision(_os.environ.get("A2C_PRECISION", "1"))     # validated like any other caller
 
 
 def get_precision():
@@ -71,6 +76,16 @@ class View:
         N, fs = states.shape[:2]
         return View(states, fs, 1, N, fs * PLANE, fs * PLANE, PLANE)
 
+    def slots(self, r0, r1):
+        """View of rollout slots [r0, r1) (all their steps): a micro-batch of the update."""
+        assert 0 <= r0 < r1 <= self.R
+        base = self.base.view(-1)[r0 * self.c.stride_r:]
+        pf = None
+        if self.pflag is not None:
+            pf = self.pflag.view(-1)[r0 * self.c.pflag_stride_r:]
+        return View(base, self.fs, self.T, r1 - r0, self.c.stride_r, self.c.stride_t,
+                    self.c.stride_c, pf, self.c.pflag_stride_r)
+
     def materialize(self, dtype=torch.float32):
         out = torch.empty((self.N, self.fs, 80, 80), dtype=dtype, device=self.device)
         call("a2c_states_materialize", C.byref(self.c), ptr(out),
@@ -114,6 +129,23 @@ class PlaneRing:
                  ptr(self.pflag), R, F, self.P, j0, stream_ptr())
         self.started = True
 
+    def push_rows(self, rows, reset, first_frame_index=0, layout=0):
+        """Stage 1 from a device staging buffer of FrameIngest: rows u8 [R, F, bytes_per_frame]
+        in staging ``layout`` (0: the 80 selected rows, 1: the cropped band, 2: whole frames),
+        reset u8 [R, F] on the device."""
+        require_cuda(rows, reset)
+        R, F = rows.shape[:2]
+        assert R == self.R and rows.dtype == torch.uint8 and rows.dim() == 3
+        assert rows.shape[2] == call("a2c_obs_ingest_bytes_per_frame", layout)
+        assert reset.shape == (R, F) and reset.dtype == torch.uint8
+        assert rows.is_contiguous() and reset.is_contiguous()
+        if F == 0:
+            return
+        call("a2c_obs_prep_stack_rows", ptr(rows), ptr(reset), ptr(self.planes), ptr(self.pflag),
+             R, F, self.P, self.fs - 1 + first_frame_index, layout, stream_ptr(),
+             tag="a2c_obs_prep_stack_rows|bytes|%dx%d" % (R, F), work=44800 * R * F)
+        self.started = True
+
     def carry(self):
         call("a2c_ring_carry", ptr(self.planes), ptr(self.pflag), self.R, self.P, self.fs,
              stream_ptr())
@@ -128,6 +160,62 @@ class PlaneRing:
     def state_at(self, t):
         """View of the single state index t of every slot (e.g. t = T: bootstrap state)."""
         return self.view(T=1, t0=t)
+
+
+class FrameIngest:
+    """Pipelined host -> device ingest of whole rollouts for stage 1.
+
+    ``prefetch(frames, reset)`` enqueues, on a private copy stream, ONE asynchronous copy from
+    pinned host memory into a device staging buffer, so it runs under the previous update's
+    kernels; ``commit(ring)`` makes the compute stream wait for that copy and runs stage 1 from
+    the staging buffer.  ``layout`` picks what crosses PCIe (see a2c_obs_ingest_rows_async):
+    0 = only the 80 selected rows of each frame (38 % of the bytes, 480-byte DMA rows), 1 = the
+    cropped band of each frame (76 %, one 76 KB run per frame), 2 = whole frames.  ``depth``
+    staging buffers are cycled; a buffer is overwritten only after the stage-1 launch that read
+    it has finished (event on the compute stream)."""
+
+    def __init__(self, R, F, device, depth=2, layout=1):
+        self.R, self.F, self.device, self.layout = R, F, device, layout
+        self.stream = torch.cuda.Stream(device=device)
+        self.frame_bytes = int(call("a2c_obs_ingest_bytes_per_frame", layout))
+        self.rows = [torch.empty((R, F, self.frame_bytes), dtype=torch.uint8, device=device)
+                     for _ in range(depth)]
+        self.reset = [torch.empty((R, F), dtype=torch.uint8, device=device) for _ in range(depth)]
+        self.copied = [torch.cuda.Event() for _ in range(depth)]
+        self.consumed = [None] * depth
+        self.head = 0            # next buffer to fill
+        self.tail = 0            # next buffer to commit
+        self.pending = 0
+        self.bytes_per_prefetch = R * F * (self.frame_bytes + 1)
+
+    def prefetch(self, frames_host, reset_host):
+        assert self.pending < len(self.rows), "FrameIngest: all staging buffers are in flight"
+        if not (frames_host.is_pinned() and reset_host.is_pinned()):
+            raise _lib.A2CError("host frames / reset must be pinned (tensor.pin_memory())")
+        assert frames_host.shape == (self.R, self.F, 210, 160, 3) and frames_host.is_contiguous()
+        assert reset_host.shape == (self.R, self.F) and reset_host.dtype == torch.uint8
+        k = self.head
+        if self.consumed[k] is not None:
+            self.stream.wait_event(self.consumed[k])
+        with torch.cuda.stream(self.stream):
+            call("a2c_obs_ingest_rows_async", ptr(frames_host), ptr(self.rows[k]),
+                 self.R * self.F, self.layout, C.c_void_p(self.stream.cuda_stream))
+            self.reset[k].copy_(reset_host, non_blocking=True)
+            self.copied[k].record(self.stream)
+        self.head = (k + 1) % len(self.rows)
+        self.pending += 1
+
+    def commit(self, ring, first_frame_index=0):
+        assert self.pending > 0, "FrameIngest.commit without a prefetch"
+        k = self.tail
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self.copied[k])
+        ring.push_rows(self.rows[k], self.reset[k], first_frame_index, self.layout)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.consumed[k] = ev
+        self.tail = (k + 1) % len(self.rows)
+        self.pending -= 1
 
 
 # --------------------------------------------------------------------------
@@ -158,7 +246,8 @@ def delta_scan(rewards, dones, values, gamma, lambda_, want_stats=True):
     rets = torch.empty_like(deltas)
     stats = torch.zeros(4, dtype=torch.float64, device=dev) if want_stats else None
     call("a2c_delta_scan", ptr(rewards), ptr(dones), ptr(values), ptr(deltas), ptr(advs), ptr(rets),
-         ptr(stats), R, T, float(gamma), float(gamma * lambda_), stream_ptr())
+         ptr(stats), R, T, float(gamma), float(gamma * lambda_), stream_ptr(),
+         tag="a2c_delta_scan|bytes|%dx%d" % (R, T), work=28 * R * T)
     return deltas, advs, rets, stats
 
 
@@ -170,6 +259,23 @@ def discount(array, dones, factor, stats=None):
     call("a2c_discount", ptr(a), ptr(d), ptr(out), ptr(stats), a.numel(), float(factor),
          stream_ptr())
     return out
+
+
+def discount2(deltas, rewards, dones, gamma_lambda, gamma, stats=None):
+    """advs = discount(deltas, dones, gamma*lambda) and (rewards not None) returns =
+    discount(rewards, dones, gamma) in one launch; stats f64 [4] accumulates their sums."""
+    require_cuda(deltas, rewards, dones)
+    d = deltas.reshape(-1).contiguous().float()
+    dn = dones.reshape(-1).contiguous().float()
+    advs = torch.empty_like(d)
+    r = rets = None
+    if rewards is not None:
+        r = rewards.reshape(-1).contiguous().float()
+        rets = torch.empty_like(d)
+    call("a2c_discount2", ptr(d), ptr(r), ptr(dn), ptr(advs), ptr(rets), ptr(stats), d.numel(),
+         float(gamma_lambda), float(gamma), stream_ptr(),
+         tag="a2c_discount2|bytes|%d" % d.numel(), work=(12 + 8 * (rewards is not None)) * d.numel())
+    return advs, rets
 
 
 def loss_fwd_bwd(logits, vals, actions, advs, returns, adv_stats, hyps, n_global=None,
@@ -188,7 +294,7 @@ def loss_fwd_bwd(logits, vals, actions, advs, returns, adv_stats, hyps, n_global
     out = torch.empty(4, dtype=torch.float32, device=logits.device)
     call("a2c_loss_fwd_bwd", ptr(logits), ptr(vals), ptr(actions), ptr(advs), ptr(returns),
          ptr(adv_stats), ptr(ret_norm), C.byref(cfg), ptr(dlogits), ptr(dvals), ptr(out), N, A,
-         stream_ptr())
+         stream_ptr(), tag="a2c_loss_fwd_bwd|bytes|%dx%d" % (N, A), work=(24 + 8 * A) * N)
     return dlogits, dvals, out
 
 
@@ -197,15 +303,16 @@ def loss_fwd_bwd(logits, vals, actions, advs, returns, adv_stats, hyps, n_global
 # --------------------------------------------------------------------------
 
 def gemm(A, sam, sak, B, sbk, sbn, M, N, K, out=None, ldc=None, bias=None, relu=False, beta=0,
-         precision=None, c_offset=0):
-    """out[M, N] (+)= A * B with explicit element strides (see a2c_gemm)."""
+         precision=None, c_offset=0, cmask=None):
+    """out[M, N] (+)= A * B with explicit element strides (see a2c_gemm); cmask (laid out like
+    out): out = cmask > 0 ? value : 0 (a2c_gemm_masked)."""
     dev = A.device
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=dev)
         ldc = N
     ws = workspace(dev)
     cptr = C.c_void_p(out.data_ptr() + 4 * c_offset)
-    call("a2c_gemm", ptr(A), sam, sak, ptr(B), sbk, sbn, cptr, ldc, ptr(bias), M, N, K,
+    call("a2c_gemm_masked", ptr(A), sam, sak, ptr(B), sbk, sbn, cptr, ldc, ptr(bias), ptr(cmask), M, N, K,
          1 if relu else 0, beta, _PRECISION if precision is None else precision, ptr(ws),
          ws.numel(), stream_ptr(), tag="a2c_gemm|flops|%dx%dx%d" % (M, N, K), work=2.0 * M * N * K)
     return out
@@ -224,10 +331,12 @@ def relu_bwd(dY, Y):
 
 
 class LinearFn(torch.autograd.Function):
-    """y = relu?(x W^T + b); x [M, K], W [N, K] (nn.Linear layout)."""
+    """y = relu?(x W^T + b); x [M, K], W [N, K] (nn.Linear layout).  ``x_relu``: x is the output
+    of a ReLU whose mask the input gradient applies itself (dx = dy W * (x > 0)), so the layer
+    below receives an already-masked gradient (see ConvStackFn)."""
 
     @staticmethod
-    def forward(ctx, x, W, b, relu):
+    def forward(ctx, x, W, b, relu, x_relu=False):
         require_cuda(x, W, b)
         x = x.contiguous()
         M, K = x.shape
@@ -235,6 +344,7 @@ class LinearFn(torch.autograd.Function):
         y = gemm(x, K, 1, W, 1, K, M, N, K, bias=b, relu=relu)
         ctx.save_for_backward(x, W, y if relu else None)
         ctx.relu = relu
+        ctx.x_relu = x_relu
         ctx.has_bias = b is not None
         return y
 
@@ -248,12 +358,13 @@ class LinearFn(torch.autograd.Function):
         N = W.shape[0]
         dx = dW = db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm(dy, N, 1, W, K, 1, M, K, N)            # dy [M,N] * W [N,K]
+            dx = gemm(dy, N, 1, W, K, 1, M, K, N,            # dy [M,N] * W [N,K]
+                      cmask=x if ctx.x_relu else None)
         if ctx.needs_input_grad[1]:
             dW = gemm(dy, 1, N, x, K, 1, N, K, M)            # dy^T [N,M] * x [M,K]
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy, M, N)
-        return dx, dW, db, None
+        return dx, dW, db, None, None
 
 
 class LinearStateFn(torch.autograd.Function):
@@ -265,8 +376,9 @@ class LinearStateFn(torch.autograd.Function):
         N = W.shape[0]
         assert W.shape[1] == view.fs * PLANE and W.is_contiguous()
         y = torch.empty((view.N, N), dtype=torch.float32, device=W.device)
+        ws = workspace(W.device)
         call("a2c_linear_state_fwd", C.byref(view.c), ptr(W), ptr(b), ptr(y), view.R, N,
-             1 if relu else 0, stream_ptr(), tag="a2c_linear_state_fwd|flops|%dx%d" % (view.N, N),
+             1 if relu else 0, ptr(ws), ws.numel(), stream_ptr(), tag="a2c_linear_state_fwd|flops|%dx%d" % (view.N, N),
              work=2.0 * view.N * N * view.fs * PLANE)
         ctx.view = view
         ctx.save_for_backward(W, y if relu else None)
@@ -367,6 +479,103 @@ class Conv2dFn(torch.autograd.Function):
         return dx, dW, db, None, None, None
 
 
+class ConvStackFn(torch.autograd.Function):
+    """A stack of Conv2d + ReLU layers (``convs`` of ConvModel / GRUModel / A3CModel,
+    a2c/models.py:98,312,685) as ONE autograd node, so that the backward pass can apply every
+    ReLU mask where the masked gradient is born:
+
+      * the node receives the gradient of its last ReLU output ALREADY masked (``premasked``:
+        the Linear layer above applied ``x > 0`` in its input-gradient GEMM), or masks it once;
+      * layer l's input gradient kernel writes dX * (X > 0) -- X being layer l-1's ReLU output --
+        and the per-channel sums of that product, i.e. layer l-1's masked output gradient and
+        bias gradient (a2c_conv2d_bwd_data_relu);
+      * so no weight- or input-gradient kernel reads a forward output as a mask, and the
+        separate bias-gradient pass over dY disappears for all layers but the last.
+
+    apply(x, premasked, (stride, pad) per layer..., W0, b0, W1, b1, ...) -> features [N, C, h, w].
+    x: tensor or View (first layer reads the uint8 ring)."""
+
+    @staticmethod
+    def forward(ctx, x, premasked, geom, *params):
+        L = len(geom)
+        assert len(params) == 2 * L
+        is_view = isinstance(x, View)
+        acts, shapes = [], []
+        cur = x
+        for l in range(L):
+            W, b = params[2 * l], params[2 * l + 1]
+            require_cuda(W, b)
+            Cout, Cin, K, _ = W.shape
+            stride, pad = geom[l]
+            if l == 0 and is_view:
+                N, Hh, Ww = cur.N, 80, 80
+                assert cur.fs == Cin
+            else:
+                cur = cur.contiguous()
+                N, _, Hh, Ww = cur.shape
+            s = conv_shape(Cin, Cout, Hh, Ww, K, stride, pad)
+            y = torch.empty((N, Cout, s.OH, s.OW), dtype=torch.float32, device=W.device)
+            flops = 2.0 * N * s.OH * s.OW * Cout * Cin * K * K
+            sig = "%d:%d>%d,%dx%d,k%ds%d" % (N, Cin, Cout, Hh, Ww, K, stride)
+            first_view = l == 0 and is_view
+            call("a2c_conv2d_fwd", None if first_view else ptr(cur), C.byref(cur.c) if first_view else None,
+                 ptr(W), ptr(b), ptr(y), N, C.byref(s), 1, _PRECISION, stream_ptr(),
+                 tag="a2c_conv2d_fwd|flops|" + sig, work=flops)
+            shapes.append((s, flops, sig))
+            acts.append(y)
+            cur = y
+        ctx.shapes, ctx.N, ctx.L = shapes, N, L
+        ctx.premasked, ctx.precision, ctx.is_view = premasked, _PRECISION, is_view
+        ctx.view = x if is_view else None
+        ctx.save_for_backward(*(([] if is_view else [x]) + acts + list(params[0::2])))
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, dy):
+        L, N, prec = ctx.L, ctx.N, ctx.precision
+        saved = list(ctx.saved_tensors)
+        x0 = None if ctx.is_view else saved.pop(0)
+        acts, Ws = saved[:L], saved[L:]
+        dy = dy.contiguous()
+        if not ctx.premasked:
+            dy = relu_bwd(dy, acts[-1])
+        dev = dy.device
+        grads = [None] * (2 * L)
+        ws0 = workspace(dev)
+        # bias gradient of the last layer: channel sums of its masked output gradient
+        sL = ctx.shapes[-1][0]
+        db = torch.empty(sL.Cout, dtype=torch.float32, device=dev)
+        call("a2c_channel_sum", ptr(dy), None, ptr(db), N, sL.Cout, sL.OH * sL.OW, ptr(ws0), ws0.numel(),
+             stream_ptr())
+        grads[2 * (L - 1) + 1] = db
+        dx0 = None
+        for l in range(L - 1, -1, -1):
+            s, flops, sig = ctx.shapes[l]
+            W = Ws[l]
+            xin = acts[l - 1] if l > 0 else x0
+            # weight gradient (bias gradients come from the epilogues above / the channel sum)
+            dW = torch.empty_like(W)
+            need = call("a2c_conv2d_bwd_weight_workspace", C.byref(s))
+            ws = workspace(dev, max(need, 64 << 20))
+            first_view = l == 0 and ctx.is_view
+            call("a2c_conv2d_bwd_weight", None if first_view else ptr(xin),
+                 C.byref(ctx.view.c) if first_view else None, ptr(dy), None, ptr(dW), None, N, C.byref(s),
+                 ptr(ws), ws.numel(), prec, stream_ptr(), tag="a2c_conv2d_bwd_weight|flops|" + sig, work=flops)
+            grads[2 * l] = dW
+            if l > 0:
+                dx = torch.empty_like(xin)
+                dbp = torch.empty(s.Cin, dtype=torch.float32, device=dev)
+                call("a2c_conv2d_bwd_data_relu", ptr(dy), ptr(W), ptr(xin), ptr(dx), ptr(dbp), N, C.byref(s),
+                     prec, ptr(ws), ws.numel(), stream_ptr(), tag="a2c_conv2d_bwd_data|flops|" + sig, work=flops)
+                grads[2 * (l - 1) + 1] = dbp
+                dy = dx
+            elif not ctx.is_view and ctx.needs_input_grad[0]:
+                dx0 = torch.empty_like(x0)
+                call("a2c_conv2d_bwd_data", ptr(dy), None, ptr(W), ptr(dx0), N, C.byref(s), prec, stream_ptr(),
+                     tag="a2c_conv2d_bwd_data|flops|" + sig, work=flops)
+        return (dx0, None, None) + tuple(grads)
+
+
 class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta):
@@ -464,6 +673,92 @@ class GRUCellFn(torch.autograd.Function):
         call("a2c_colsum", ptr(dgzr), ptr(dbf), B, 2 * H, stream_ptr())
         call("a2c_colsum", ptr(dgc), ptr(dbf[2 * H:]), B, H, stream_ptr())
         return dx, dh, dWx, dWh, db, None
+
+
+class GRUSequenceFn(torch.autograd.Function):
+    """T steps of the reference's GRU cell with the masked carry of BPTT
+    (a2c/updater.py:139-169: ``h <- cell(x_t, h); h <- h * (1 - done_t)``) as ONE autograd node.
+
+    Everything that does not depend on the recurrence is hoisted out of the time loop and runs as
+    large GEMMs over all T*R rows: the input products x_t W_x + b (forward), and in backward the
+    weight gradients dW_x = sum_t x_t^T G_t, dW_h = sum_t h_t^T G_t (one split-K GEMM each, K =
+    T*R), the bias gradient and dx = G W_x^T.  The loop itself keeps 5 launches per step forward
+    (h W_h0, h W_h1, gates, (r*h) W_h2, gates) and 6 backward, all on preallocated [T, R, *]
+    buffers.  x [T, R, X] time-major, h0 [R, H], keep [T, R] = 1 - done -> hnew [T, R, H]."""
+
+    @staticmethod
+    def forward(ctx, x, h0, Wx, Wh, b, keep):
+        require_cuda(x, h0, Wx, Wh, b, keep)
+        x, h0, keep = x.contiguous(), h0.contiguous(), keep.contiguous()
+        T, B, X = x.shape
+        H = h0.shape[1]
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        gx = torch.empty((T * B, 3 * H), **f32)
+        bflat = b.reshape(3, H)
+        xf = x.view(T * B, X)
+        for g in range(3):      # x.mm(W_x[g]) + b[g] for every step at once
+            gemm(xf, X, 1, Wx[g], H, 1, T * B, H, X, out=gx, ldc=3 * H, bias=bflat[g], c_offset=g * H)
+        gx = gx.view(T, B, 3 * H)
+        hprev = torch.empty((T + 1, B, H), **f32)        # hprev[t] = carry entering step t
+        hprev[0].copy_(h0)
+        z, r, rh, cand, hnew = (torch.empty((T, B, H), **f32) for _ in range(5))
+        gh = torch.empty((B, 2 * H), **f32)
+        gc = torch.empty((B, H), **f32)
+        for t in range(T):
+            h = hprev[t]
+            for g in range(2):
+                gemm(h, H, 1, Wh[g], H, 1, B, H, H, out=gh, ldc=2 * H, c_offset=g * H)
+            call("a2c_gru_gates1", ptr(gx[t]), ptr(gh), ptr(h), ptr(z[t]), ptr(r[t]), ptr(rh[t]), B, H,
+                 stream_ptr())
+            gemm(rh[t], H, 1, Wh[2], H, 1, B, H, H, out=gc, ldc=H)
+            call("a2c_gru_gates2", ptr(gx[t]), ptr(gc), ptr(h), ptr(z[t]), ptr(keep[t]), ptr(cand[t]),
+                 ptr(hnew[t]), ptr(hprev[t + 1]), B, H, stream_ptr())
+        ctx.save_for_backward(x, Wx, Wh, keep, hprev, z, r, rh, cand)
+        return hnew
+
+    @staticmethod
+    def backward(ctx, dhnew):
+        x, Wx, Wh, keep, hprev, z, r, rh, cand = ctx.saved_tensors
+        T, B, X = x.shape
+        H = hprev.shape[2]
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        dhnew = dhnew.contiguous()
+        dgzr = torch.empty((T, B, 2 * H), **f32)         # z / r pre-activation gradients of every step
+        dgc = torch.empty((T, B, H), **f32)              # candidate pre-activation gradients
+        dz = torch.empty((B, H), **f32)
+        drh = torch.empty((B, H), **f32)
+        dh = [torch.empty((B, H), **f32), torch.empty((B, H), **f32)]
+        carry = None                                     # d loss / d hprev[t + 1]
+        for t in range(T - 1, -1, -1):
+            h, cur = hprev[t], dh[t & 1]
+            call("a2c_gru_gates2_bwd", ptr(dhnew[t]), ptr(carry), ptr(keep[t]), ptr(h), ptr(z[t]),
+                 ptr(cand[t]), ptr(dgc[t]), ptr(dz), ptr(cur), B, H, stream_ptr())
+            gemm(dgc[t], H, 1, Wh[2], 1, H, B, H, H, out=drh, ldc=H)            # dgc * Wh2^T
+            call("a2c_gru_gates1_bwd", ptr(drh), ptr(dz), ptr(h), ptr(z[t]), ptr(r[t]), ptr(dgzr[t]),
+                 ptr(cur), B, H, stream_ptr())
+            G = dgzr[t].view(-1)
+            gemm(G, 2 * H, 1, Wh[0], 1, H, B, H, H, out=cur, ldc=H, beta=1)
+            gemm(G[H:], 2 * H, 1, Wh[1], 1, H, B, H, H, out=cur, ldc=H, beta=1)
+            carry = cur
+        dh0 = carry
+        # hoisted: parameter and input gradients over all T*B rows
+        N = T * B
+        xf, hf, rhf = x.view(N, X), hprev[:T].reshape(N, H), rh.view(N, H)
+        Gzr, Gc = dgzr.view(-1), dgc.view(-1)
+        gsrc = [(Gzr, 2 * H), (Gzr[H:], 2 * H), (Gc, H)]
+        dWx, dWh = torch.empty_like(Wx), torch.empty_like(Wh)
+        dx = torch.empty((N, X), **f32)
+        for g, (Gp, ld) in enumerate(gsrc):
+            gemm(Gp, ld, 1, Wx[g], 1, H, N, X, H, out=dx, ldc=X, beta=0 if g == 0 else 1)
+            gemm(xf, 1, X, Gp, ld, 1, X, H, N, out=dWx, ldc=H, c_offset=g * X * H)
+            gemm(hf if g < 2 else rhf, 1, H, Gp, ld, 1, H, H, N, out=dWh, ldc=H, c_offset=g * H * H)
+        db = torch.empty((3, 1, H), **f32)
+        dbf = db.view(-1)
+        call("a2c_colsum", ptr(dgzr), ptr(dbf), N, 2 * H, stream_ptr())
+        call("a2c_colsum", ptr(dgc), ptr(dbf[2 * H:]), N, H, stream_ptr())
+        return dx.view(T, B, X), dh0, dWx, dWh, db, None
 
 
 # --------------------------------------------------------------------------

@@ -20,6 +20,7 @@ The environment side is a vectorised protocol (gym itself is out of scope):
 
 ``RecordedVecEnv`` plays back a synthetic trajectory (a2c_b200/synth.py).
 """
+import numpy as np
 import torch
 
 from . import ops
@@ -67,6 +68,8 @@ class Runner:
         self.ring = None
         self.h_bookmark = None
         self.ep_rew = None
+        self._stage_frames = None
+        self._stage_reset = None
 
     # ---- set-up -------------------------------------------------------------
     def attach(self, net, env):
@@ -97,11 +100,19 @@ class Runner:
                 fr = fr.contiguous()
             self.ring.push_frames(fr, reset.to(torch.uint8).reshape(R, 1).contiguous(), index)
         else:
+            # host frames: staged through ONE persistent pinned buffer (allocated once), which the
+            # stage-1 kernel reads zero-copy; the _host entry synchronises before returning, so the
+            # buffer is free again when the next step's frames arrive
             fr = frames.reshape(R, 1, 210, 160, 3)
             if not (fr.is_contiguous() and fr.is_pinned()):
-                fr = fr.contiguous().pin_memory()
-            rs = reset.to(torch.uint8).reshape(R, 1).cpu().pin_memory()
-            self.ring.push_frames(fr, rs, index)
+                if self._stage_frames is None:
+                    self._stage_frames = torch.empty((R, 1, 210, 160, 3), dtype=torch.uint8).pin_memory()
+                self._stage_frames.copy_(fr)
+                fr = self._stage_frames
+            if self._stage_reset is None:
+                self._stage_reset = torch.empty((R, 1), dtype=torch.uint8).pin_memory()
+            self._stage_reset.copy_(reset.to(torch.uint8).reshape(R, 1))
+            self.ring.push_frames(fr, self._stage_reset, index)
 
     def run(self, net):
         """a2c/runner.py:147-172: serve rollouts until the process is terminated."""
@@ -145,7 +156,6 @@ class Runner:
             rew = torch.as_tensor(rew, dtype=torch.float32, device=dev)
             reset = torch.as_tensor(done, device=dev).bool()
             done = reset | (rew != 0) if pong else reset                     # runner.py:212-214
-            self.ep_rew += rew
             if h is not None:
                 h = h * (~done).float()[:, None]                             # runner.py:218-220
             rew_v[:, t] = rew
@@ -159,6 +169,10 @@ class Runner:
         else:
             self.values[:, T] = net(view)[0].reshape(-1)
         act_v.copy_(actions_dev)
+        # raw per-step rewards / done flags for the episode-reward EMA (runner.py:211-217): taken
+        # BEFORE stage 2 folds the bootstrap into rewards[end] and forces dones[end] = 1
+        raw = torch.stack([rew_v.to(dev, torch.float32), done_v.to(dev, torch.float32)]) \
+            if self.rew_q is not None else None
         # stage 2: deltas, bootstrap fold, dones[end] = 1 (runner.py:228-245)
         r_c, d_c = rew_v.reshape(-1), done_v.reshape(-1)
         contiguous_slot = r_c.data_ptr() == rew_v.data_ptr() and r_c.is_cuda
@@ -170,8 +184,10 @@ class Runner:
             rew_v.copy_(r_c.view(R, T))
             done_v.copy_(d_c.view(R, T))
         datas['deltas'][lo:hi] = deltas
-        datas['advs_hint'] = advs
-        datas['returns_hint'] = rets
+        # stage-2 by-products: the Updater uses them (instead of re-running both scans) only
+        # when they cover exactly the buffer it is given (it checks n, gamma, lambda_)
+        datas['scan'] = {'n': R * T, 'advs': advs, 'returns': rets, 'stats': stats,
+                         'gamma': hyps['gamma'], 'lambda_': hyps['lambda_'], 'block': (lo, hi)}
         # states: the ring view is what our Updater consumes; the fp32 tensor of
         # a2c/runner.py:199 is materialised only when the caller provided one
         self.datas_view = self.ring.view(T)
@@ -180,26 +196,36 @@ class Runner:
         if 'states' in datas and torch.is_tensor(datas['states']):
             st = self.datas_view.materialize(torch.float32)
             datas['states'][lo:hi] = st
-        self._reward_ema(rew_v, done_v)
+        self._reward_ema(raw)
         self._needs_carry = True       # bookmark (runner.py:246) applied lazily: the ring view
         if h is not None:              # handed to the Updater must stay intact until then
             self.h_bookmark = h
 
-    def _reward_ema(self, rew_v, done_v):
-        """runner.py:215-217: rew_q holds an EMA of finished-episode rewards."""
-        if self.rew_q is None:
+    def _reward_ema(self, raw):
+        """runner.py:211-217: ``ep_rew`` accumulates the RAW step rewards of every env and, at
+        each done (true done or Pong point), ``rew_q`` <- .99*rew_q + .01*ep_rew and ep_rew <- 0.
+        The reference's env processes interleave arbitrarily; here events are applied time-major
+        (step t of every env before step t+1, envs in index order).  One D2H copy per rollout;
+        the EMA over the K events of the rollout is evaluated in closed form."""
+        if self.rew_q is None or raw is None:
             return
-        rew = rew_v.cpu()
-        done = done_v.cpu()
-        ep = self.ep_rew.cpu() - rew.sum(1)      # value before this rollout
-        ema = self.rew_q.get()
+        rew, done = raw.cpu().double().numpy()                  # [R, T] each
+        ep = self.ep_rew.cpu().double().numpy().copy()
+        events = []
         for t in range(rew.shape[1]):
-            ep = ep + rew[:, t]
-            for r in torch.nonzero(done[:, t]).flatten().tolist():
-                ema = .99 * ema + .01 * float(ep[r])
-                ep[r] = 0
+            ep += rew[:, t]
+            hit = done[:, t] != 0
+            if hit.any():
+                events.append(ep[hit].copy())
+                ep[hit] = 0.0
+        ema = self.rew_q.get()
+        if events:
+            x = np.concatenate(events)
+            k = len(x)
+            w = 0.99 ** np.arange(k - 1, -1, -1, dtype=np.float64)
+            ema = float(0.99 ** k * float(ema) + 0.01 * float((w * x).sum()))
         self.rew_q.put(ema)
-        self.ep_rew = ep.to(self.device)
+        self.ep_rew = torch.from_numpy(ep).float().to(self.device)
 
 
 def make_shared_data(R, T, fs, device, h_size=None, with_states=True):

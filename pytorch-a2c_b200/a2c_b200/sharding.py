@@ -52,11 +52,39 @@ def shard_rollout(shared_data, n_slots, n_tsteps, rank_=None, world=None):
     return out
 
 
+def _needs_host_staging(t):
+    # gloo (CPU tests, or several ranks sharing one GPU in the -m gpu suite) reduces host tensors
+    return t.is_cuda and dist.get_backend() == "gloo"
+
+
 def allreduce_sum_(t):
     """In-place SUM over ranks; identity for a single process."""
     if world_size() > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if _needs_host_staging(t):
+            h = t.detach().cpu()
+            dist.all_reduce(h, op=dist.ReduceOp.SUM)
+            t.copy_(h)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return t
+
+
+class _Done:
+    def wait(self):
+        return True
+
+
+def allreduce_sum_async(t):
+    """Starts an in-place SUM over ranks and returns a handle with ``wait()``.  Under NCCL the
+    collective is enqueued behind the work already on the current stream and runs on NCCL's own
+    stream, i.e. concurrently with kernels launched afterwards; ``wait()`` makes the current
+    stream wait for it (no host synchronisation)."""
+    if world_size() == 1:
+        return _Done()
+    if _needs_host_staging(t):
+        allreduce_sum_(t)
+        return _Done()
+    return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
 
 
 def global_count(n_local):

@@ -3,8 +3,12 @@ done by the stage 2-4 kernels.
 
 Differences from the reference are additive: ``compute_gradients`` (gradient
 only, for parity tests), env-sharded data parallelism when torch.distributed is
-initialised, and ``shared_data['states']`` may also be a
-uint8 tensor or an ``ops.View`` of the stage-1 plane ring.
+initialised, micro-batching over rollout slots (the
+reference sees all N transitions at once, a2c/updater.py:33-137; ConvModel keeps
+~3.4 MB of activations per transition, so C5's 81,920 transitions are processed
+in chunks whose gradients accumulate in the flat buffer), and
+``shared_data['states']`` may also be a uint8 tensor or an ``ops.View`` of the
+stage-1 plane ring.
 """
 import torch
 import torch.optim as optim
@@ -58,9 +62,13 @@ class _FlatParams:
 
 
 class Updater:
-    def __init__(self, net, hyps):
+    def __init__(self, net, hyps, data_parallel=True):
+        """``data_parallel=False`` keeps this Updater single-process even when a
+        torch.distributed group exists (used to check the sharded update against the
+        full-batch one on the same hardware)."""
         self.net = net
         self.hyps = hyps
+        self.data_parallel = data_parallel
         self.is_discrete = hyps['is_discrete']
         if not self.is_discrete:
             raise NotImplementedError("continuous actions are out of scope")
@@ -77,10 +85,15 @@ class Updater:
         self.ret_std = None
         self._step = 0
         self._count_cache = (None, None)
+        self.last_chunks = 1            # micro-batches of the last update
+        self.last_allreduce = None      # {"bytes", "buckets", "overlapped_bytes"} of the last update
 
     # ---- distributed helpers (env-sharded ranks) ----------
-    _world = staticmethod(sharding.world_size)
-    _allreduce = staticmethod(sharding.allreduce_sum_)
+    def _world(self):
+        return sharding.world_size() if self.data_parallel else 1
+
+    def _allreduce(self, t):
+        return sharding.allreduce_sum_(t) if self.data_parallel else t
 
     def _n_global(self, n_local):
         """Transitions over all ranks; one tiny all-reduce, cached per local size."""
@@ -96,15 +109,44 @@ class Updater:
             return t
         return t if t.is_cuda else t.to(self.device, non_blocking=True)
 
-    def _forward(self, states, shared_data, dones):
+    def _forward(self, states, h_states, dones, R):
         hyps, net = self.hyps, self.net
-        if 'h_states' in shared_data:
-            h_states = self._to_dev(shared_data['h_states'])
+        if h_states is not None:
             if hyps['use_bptt']:
-                return self.bptt(states, h_states, dones)
+                return self.bptt(states, h_states, dones, n_rollouts=R)
             vals, logits, _ = net(states, h_states)
             return vals, logits
         return net(states)
+
+    # ---- micro-batching -----------------------------------------------------------
+    def _chunk_slots(self, R, T):
+        """Rollout slots per micro-batch: ``hyps['update_chunk_slots']`` or as many as fit in
+        ~45 % of the free device memory by the model's activation estimate."""
+        c = try_key(self.hyps, 'update_chunk_slots', None)
+        if c is None:
+            est = getattr(self.net, 'activation_bytes_per_state', None)
+            per = est() if callable(est) else 4 << 20
+            free, _ = torch.cuda.mem_get_info(self.device)
+            free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+            c = int(0.45 * free // (per * T))
+        return max(1, min(R, int(c)))
+
+    @staticmethod
+    def _slot_slice(x, r0, r1, T):
+        if x is None:
+            return None
+        if isinstance(x, ops.View):
+            return x.slots(r0, r1)
+        return x[r0 * T:r1 * T]
+
+    def _big_bucket(self):
+        """(offset, numel) of the one parameter that dominates the flat buffer (ConvModel's
+        resize_emb.0.weight: 98 % of 209 MB), or None.  Its gradient is final early in backward
+        (it belongs to a late layer), so its all-reduce can run under the conv backward."""
+        f = self.flat
+        i = max(range(len(f.params)), key=lambda j: f.params[j].numel())
+        n = f.params[i].numel()
+        return (i, f.offsets[i], n) if n >= 0.5 * f.numel and n >= (1 << 22) else None
 
     def compute_gradients(self, shared_data):
         """update_model up to and including backward (a2c/updater.py:63-128).
@@ -113,28 +155,62 @@ class Updater:
         hyps, net = self.hyps, self.net
         net.req_grads(True)
         self.flat.rebind_grads()
-        states = self._to_dev(shared_data['states_view'] if 'states_view' in shared_data
-                              else shared_data['states'])
         rewards = self._to_dev(shared_data['rewards']).reshape(-1).float()
         dones = self._to_dev(shared_data['dones']).reshape(-1).float()
         actions = self._to_dev(shared_data['actions']).reshape(-1)
         deltas = self._to_dev(shared_data['deltas']).reshape(-1).float()
         N = deltas.numel()
+        # the ring view is used only when it describes exactly these N transitions (a Runner
+        # injects the view of ITS last block; buffers holding several blocks use 'states')
+        view = shared_data.get('states_view')
+        if isinstance(view, ops.View) and view.N == N:
+            states = view
+        else:
+            states = self._to_dev(shared_data['states'])
+            if states is None:
+                raise ops._lib.A2CError("shared_data['states'] is missing and 'states_view' does not "
+                                        "cover the %d transitions of this update" % N)
+            n_states = states.N if isinstance(states, ops.View) else states.shape[0]
+            if n_states != N:
+                raise ops._lib.A2CError("states hold %d transitions, deltas %d" % (n_states, N))
+        h_states = self._to_dev(shared_data['h_states']) if 'h_states' in shared_data else None
+        T = hyps['n_tsteps']
+        if N % T:
+            raise ops._lib.A2CError("N=%d is not a multiple of n_tsteps=%d" % (N, T))
+        R = N // T
         world = self._world()
         n_global = self._n_global(N)
+        nstep = bool(hyps['use_nstep_rets'])
 
-        stats = torch.zeros(4, dtype=torch.float64, device=self.device)
-        advs = ops.discount(deltas, dones, hyps['gamma'] * hyps['lambda_'], stats=stats[0:2])
-        returns = None
-        if not hyps['use_nstep_rets']:
-            returns = ops.discount(rewards, dones, hyps['gamma'], stats=stats[2:4])
+        # ---- stage 2: advantages / returns (a2c/updater.py:70-71,86-88) --------------------
+        pre = shared_data.get('scan')          # Runner / stage-2 output for exactly these buffers
+        if (isinstance(pre, dict) and pre.get('n') == N and pre['advs'].numel() == N
+                and pre.get('gamma') == hyps['gamma'] and pre.get('lambda_') == hyps['lambda_']):
+            advs, returns = pre['advs'], (None if nstep else pre['returns'])
+            stats = pre['stats'].clone()
+        else:
+            stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+            advs, returns = ops.discount2(deltas, None if nstep else rewards, dones,
+                                          hyps['gamma'] * hyps['lambda_'], hyps['gamma'], stats)
 
-        vals, logits = self._forward(states, shared_data, dones)
+        chunk = self._chunk_slots(R, T)
+        bounds = [(r0, min(R, r0 + chunk)) for r0 in range(0, R, chunk)]
+        self.last_chunks = len(bounds)
+        norm_ret = bool(try_key(hyps, 'norm_returns', False))
 
         ret_norm = None
-        if try_key(hyps, 'norm_returns', False):
-            # a2c/updater.py:89-96 (EMA of mean / unbiased std); rare path, stats on host side
-            rets = returns if returns is not None else advs + vals.detach().reshape(-1)
+        if norm_ret:
+            # a2c/updater.py:89-96 (EMA of mean / unbiased std of the returns); rare path
+            if nstep:
+                # returns = advs + vals need every forward first: one extra no-grad pass
+                with torch.no_grad():
+                    v_all = torch.cat([self._forward(self._slot_slice(states, a, b, T),
+                                                     self._slot_slice(h_states, a, b, T),
+                                                     dones[a * T:b * T], b - a)[0].reshape(-1)
+                                       for a, b in bounds])
+                rets = advs + v_all
+            else:
+                rets = returns
             if world > 1:
                 s = torch.stack([rets.double().sum(), (rets.double() ** 2).sum()])
                 mean, std = sharding.mean_unbiased_std(self._allreduce(s), n_global)
@@ -149,14 +225,55 @@ class Updater:
         if hyps['norm_advs']:
             self._allreduce(stats)
 
-        dlogits, dvals, out = ops.loss_fwd_bwd(logits.detach(), vals.detach(), actions, advs,
-                                               returns, stats[0:2], hyps, n_global=n_global,
-                                               ret_norm=ret_norm)
-        torch.autograd.backward([logits, vals], [dlogits, dvals.view_as(vals)])
-        self._allreduce(self.flat.grad)
-        self._allreduce(out)
-        return {"loss_terms": out, "advs": advs, "returns": returns, "vals": vals.detach(),
-                "logits": logits.detach(), "n_global": n_global}
+        # ---- stages 3 + 4 per micro-batch; gradients accumulate in the flat buffer -------------
+        big = self._big_bucket() if world > 1 else None
+        state = {"last": False, "work": None}
+        hook = None
+        if big is not None:
+            i_big, off_big, n_big = big
+
+            def _early_allreduce(param):
+                # the big bucket's gradient is complete once the last micro-batch has accumulated
+                # it: reduce it now, under the rest of the backward pass
+                if state["last"] and state["work"] is None:
+                    state["work"] = sharding.allreduce_sum_async(self.flat.grad[off_big:off_big + n_big])
+            hook = self.flat.params[i_big].register_post_accumulate_grad_hook(_early_allreduce)
+        out = None
+        vals_all, logits_all = [], []
+        try:
+            for ci, (a, b) in enumerate(bounds):
+                state["last"] = ci == len(bounds) - 1
+                sl = slice(a * T, b * T)
+                vals, logits = self._forward(self._slot_slice(states, a, b, T),
+                                             self._slot_slice(h_states, a, b, T), dones[sl], b - a)
+                dlogits, dvals, o = ops.loss_fwd_bwd(
+                    logits.detach(), vals.detach(), actions[sl], advs[sl],
+                    None if returns is None else returns[sl], stats[0:2], hyps,
+                    n_global=n_global, ret_norm=ret_norm)
+                torch.autograd.backward([logits, vals], [dlogits, dvals.view_as(vals)])
+                out = o if out is None else out + o
+                vals_all.append(vals.detach().reshape(-1))
+                logits_all.append(logits.detach())
+                del vals, logits, dlogits, dvals
+        finally:
+            if hook is not None:
+                hook.remove()
+        g = self.flat.grad
+        if world > 1:
+            if state["work"] is not None:
+                # the rest of the flat buffer: the ranges before and after the big bucket
+                self._allreduce(g[:off_big])
+                self._allreduce(g[off_big + n_big:])
+                state["work"].wait()
+                self.last_allreduce = {"bytes": 4 * g.numel(), "buckets": 3, "overlapped_bytes": 4 * n_big}
+            else:
+                self._allreduce(g)
+                self.last_allreduce = {"bytes": 4 * g.numel(), "buckets": 1, "overlapped_bytes": 0}
+            self._allreduce(out)
+        return {"loss_terms": out, "advs": advs, "returns": returns,
+                "vals": vals_all[0] if len(vals_all) == 1 else torch.cat(vals_all),
+                "logits": logits_all[0] if len(logits_all) == 1 else torch.cat(logits_all),
+                "n_global": n_global, "chunks": len(bounds)}
 
     def update_model(self, shared_data):
         """a2c/updater.py:33-137.  Returns {"Loss", "Pi_Loss", "ValLoss", "Entropy",
@@ -174,6 +291,7 @@ class Updater:
         """clip_grad_norm_ + optimizer.step + zero_grad (a2c/updater.py:129-132)
         as two kernels over the flat buffers.  The torch optimizer object in
         ``self.optim`` owns the hyper-parameters and (as views) the state."""
+        self._sync_optim_state()
         f, group = self.flat, self.optim.param_groups[0]
         self._step += 1
         f.sumsq.zero_()
@@ -192,14 +310,34 @@ class Updater:
             if 'step' in st:
                 st['step'] += 1
 
+    def _sync_optim_state(self):
+        """``optim.load_state_dict`` (the reference's resume path, a2c/training.py:126-127)
+        replaces the per-parameter state tensors with fresh ones.  The fused step reads the
+        flat buffers, so when a state tensor is no longer our view its values are copied in,
+        the step counter is restored and the views are bound again."""
+        f, opt = self.flat, self.optim
+        key1 = 'square_avg' if isinstance(opt, optim.RMSprop) else 'exp_avg'
+        stale = False
+        for i, p in enumerate(f.params):
+            st = opt.state.get(p)
+            if not st or key1 not in st:
+                stale = stale or bool(st)
+                continue
+            if st[key1].data_ptr() != f.view_of(f.state1, i).data_ptr():
+                stale = True
+                break
+        if stale:
+            steps = [float(st['step']) for st in opt.state.values() if 'step' in st]
+            self._bind_state(opt)
+            if steps:
+                self._step = int(max(steps))
+
     # ---- reference API ----------------------------------------------------------
-    def bptt(self, states, h_states, dones):
-        """a2c/updater.py:139-169."""
-        hyps = self.hyps
-        R, T = hyps['n_rollouts'], hyps['n_tsteps']
-        w = self._world()
-        if w > 1:
-            R = dones.numel() // T
+    def bptt(self, states, h_states, dones, n_rollouts=None):
+        """a2c/updater.py:139-169.  ``n_rollouts`` defaults to the number of rollout slots in
+        ``dones`` (the reference reads hyps['n_rollouts']; a rank or a micro-batch holds fewer)."""
+        T = self.hyps['n_tsteps']
+        R = dones.numel() // T if n_rollouts is None else n_rollouts
         h0 = h_states.view(R, T, -1)[:, 0].contiguous()
         return self.net.bptt_forward(states, h0, dones, R, T)
 
@@ -254,12 +392,12 @@ class Updater:
             st = opt.state[p]
             s1 = f.view_of(f.state1, i)
             key1 = 'square_avg' if is_rms else 'exp_avg'
-            if not fresh and key1 in st:
+            if not fresh and key1 in st and st[key1].data_ptr() != s1.data_ptr():
                 s1.copy_(st[key1])
             st[key1] = s1
             if not is_rms:
                 s2 = f.view_of(f.state2, i)
-                if not fresh and 'exp_avg_sq' in st:
+                if not fresh and 'exp_avg_sq' in st and st['exp_avg_sq'].data_ptr() != s2.data_ptr():
                     s2.copy_(st['exp_avg_sq'])
                 st['exp_avg_sq'] = s2
             if 'step' not in st:

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/a2c_b200.h"
@@ -42,6 +43,22 @@ inline int num_sms() {
       n = 148;
   }
   return n;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is
+// per device, so a process-wide "done" flag would leave a second GPU without the opt-in.
+cudaError_t set_max_dynamic_smem(const void* kernel, int bytes);
+
+// Profiling knobs (stage isolation etc.) exist only in builds made with -DA2C_DEBUG_KNOBS;
+// release builds never read the environment on a launch path.
+inline int debug_knob(const char* name) {
+#ifdef A2C_DEBUG_KNOBS
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+#else
+  (void)name;
+  return 0;
+#endif
 }
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

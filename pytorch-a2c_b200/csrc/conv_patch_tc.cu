@@ -744,8 +744,7 @@ static bool make_patch_tmap(PatchParams& p, CUtensorMap* tmap) {
   memset(tmap, 0, sizeof(*tmap));
   p.use_tma = 0;
   if (p.use_view || !p.src) return true;
-  static const bool no_tma = getenv("A2C_NO_TMA") != nullptr;
-  if (no_tma) return true;
+  if (debug_knob("A2C_NO_TMA")) return true;
   if ((p.SW % 4) != 0 || (p.PW % 4) != 0 || (reinterpret_cast<uintptr_t>(p.src) & 15)) return true;
   if (p.PW > 256 || p.PH > 256 || p.SC > 256) return true;
   auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(tensormap_encoder());
@@ -767,11 +766,7 @@ static int launch_fwd_like(PatchParams& p, cudaStream_t st) {
   int bres = 0;
   if (!plan_smem(&p, AP, BP, p.nkb, &bres)) return 1;
   auto kern = conv_patch_fwd_kernel<BN, SPLIT3>;
-  static bool configured = false;
-  if (!configured) {
-    A2C_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
-    configured = true;
-  }
+  A2C_CUDA_CHECK(set_max_dynamic_smem(reinterpret_cast<const void*>(kern), smem_limit()));
   const int ntiles = p.N * p.tiles_y * p.tiles_x;
   int grid = num_sms();
   if (grid > ntiles) grid = ntiles;
@@ -895,11 +890,7 @@ static int launch_wgrad(PatchParams& p, int ntiles_n, int groups, cudaStream_t s
   int bres = 0;
   if (!plan_smem(&p, AP, BP, 0, &bres)) return 1;
   auto kern = conv_patch_wgrad_kernel<BN, SPLIT3>;
-  static bool configured = false;
-  if (!configured) {
-    A2C_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit()));
-    configured = true;
-  }
+  A2C_CUDA_CHECK(set_max_dynamic_smem(reinterpret_cast<const void*>(kern), smem_limit()));
   CUtensorMap tmap;
   make_patch_tmap(p, &tmap);
   kern<<<dim3(ntiles_n, groups), P_THREADS, patch_smem_bytes(p, 0), st>>>(tmap, p);

@@ -19,9 +19,14 @@
 //                      (Ymask > 0) is applied while the band is converted, so the masked
 //                      gradient never exists in HBM
 //
-// Weights for all taps stay resident in shared memory (hi/lo).  TMEM accumulators add with
-// truncation (tc_core.cuh), so the taps of a tile are split into `nch` short chains that the
-// drain warps sum in fp32 registers.
+// Weights for all taps stay resident in shared memory, hi and lo copies side by side along N:
+// the 3xTF32 product  x_hi*w_hi + x_hi*w_lo + x_lo*w_hi  is issued as TWO instructions,
+//     D[:, 0:2N] (+)= X_hi * [W_hi | W_lo]   (one MMA of width 2N)    and    D[:, 0:N] += X_lo * W_hi,
+// and the drain adds the two column halves.  A small-N MMA is bound by the 128 x 32 B read of
+// its A operand from shared memory, whatever N is, so two MMAs instead of
+// three cut the tensor core's shared-memory traffic per product from 3 x (4 KB + B) to
+// 2 x 4 KB + 1.5 B.  TMEM accumulators add with truncation (tc_core.cuh), so the taps of a tile
+// are split into `nch` short chains that the drain warps sum in fp32 registers.
 //
 // Replaces nn.Conv2d forward / input-gradient of a2c/models.py:98,312,685 for 3x3 pad-1 layers.
 #include <stdlib.h>
@@ -60,6 +65,7 @@ struct ShiftParams {
   int cvalid;             // real source channels (first layers: C is padded to 8, channels >= cvalid are zero)
   int nsplit;             // 2: the source has a lo part (3 MMAs per product); 1: exact in TF32 ({0,1} ring) -> 2 MMAs
   int N, C, SH, SW, ncg, ksteps;
+  int scalar_w;           // SW % 4 != 0 (10x10 / 5x5 planes): one pixel per lane, scalar loads
   int cs;                 // input class step (1, or 2 for the stride-2 forward)
   int p0y, p0x;           // plane (row r, col c, class cy,cx) <-> source (r*cs + cy - p0y, c*cs + cx - p0x)
   int PW;                 // class plane width
@@ -76,6 +82,9 @@ struct ShiftParams {
   const float* bias;
   int relu;
   float* out;
+  const float* omask;     // optional, same shape as out: out = omask > 0 ? value : 0  (the ReLU of the layer
+                          // that produced this layer's input, applied where its gradient is born)
+  double* obias;          // optional f64 [J]: per-channel sums of the (masked) output = bias gradient of that layer
   int OutH, OutW;
   int half_bytes, buf_bytes, w_half_bytes, nbuf;
   int dbg;                // A2C_SHIFT_DBG, stage isolation for profiling: 2 = no MMAs, 4 = no loads, 8 = no stores
@@ -139,14 +148,16 @@ __device__ __forceinline__ void store_split(uint8_t* dst, int half_bytes, float 
 
 // FIRST: first-layer variant (<= 4 real channels padded to one k-step, optional uint8 ring source,
 // optional 2-product split); a template flag so the general kernel's hot loops stay branch-free.
-template <int NPAD, bool FIRST>
+// MASKOUT: backward-data variant whose epilogue applies omask and accumulates obias.
+template <int NPAD, bool FIRST, bool MASKOUT = false>
 __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_constant__ ShiftParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int NCOL = NPAD / 2;                      // accumulator columns per drain warp
   constexpr int LDN = NCOL >= 16 ? 16 : 8;
-  constexpr int WBLK = NPAD * 32;                     // bytes of one (tap, kstep) weight block
+  constexpr int WBLK = 2 * NPAD * 32;                 // bytes of one (tap, kstep) weight block: [kchunk][hi n | lo n][4]
+  constexpr int NACC = 2 * NPAD;                      // TMEM columns of one accumulator chain (hi | lo halves)
   uint8_t* base = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-  uint8_t* wsm = base;                                // [hi | lo] x [tap][kstep][kchunk][n][4]
+  uint8_t* wsm = base;                                // [tap][kstep][kchunk][hi n | lo n][4]
   uint8_t* bufs = wsm + 2 * p.w_half_bytes;           // nbuf band buffers, each [hi | lo][cg][class][pos][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bufs + (size_t)p.nbuf * p.buf_bytes + 4096);  // 4 KB overrun slack
   uint64_t* patch_full = bars;                        // [2]
@@ -161,8 +172,8 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int nitems = p.N * p.nbands;
   // accumulator slots: a tile (nch chains of NPAD columns) per slot, tile i uses slot i % nslot
-  const uint32_t nslot = (SH_MAXSLOT * p.nch * NPAD <= 512) ? SH_MAXSLOT : 2;
-  const uint32_t tcols = (uint32_t)tmem_cols_pow2(nslot * p.nch * NPAD);
+  const uint32_t nslot = (SH_MAXSLOT * p.nch * NACC <= 512) ? SH_MAXSLOT : 2;
+  const uint32_t tcols = (uint32_t)tmem_cols_pow2(nslot * p.nch * NACC);
 
   if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
@@ -197,7 +208,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
                    ? __ldg(p.wt + (long long)(p.n0 + n) * p.wsn + (long long)k * p.wsk + p.taps[g].woff)
                    : 0.0f;
       }
-      store_split(wsm + (size_t)(g * p.ksteps + ks) * WBLK + kc * (NPAD * 16) + n * 16, p.w_half_bytes, v[0], v[1],
+      store_split(wsm + (size_t)(g * p.ksteps + ks) * WBLK + kc * (NACC * 16) + n * 16, NPAD * 16, v[0], v[1],
                   v[2], v[3]);
     }
     for (int n = threadIdx.x; n < NPAD; n += SH_THREADS)
@@ -217,7 +228,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
     // A lane converts 4 consecutive pixels of 4 channels: 4 LDG.128 in, the 4x4 block is
     // transposed in registers (free) and leaves as 4 + 4 STS.128 (hi, lo).  A source row is
     // NX4 float4 wide, so 32 / NX4 (row, channel group) tasks share a warp.
-    const int NX4 = p.SW >> 2;
+    const int NX4 = p.scalar_w ? p.SW : p.SW >> 2;             // lanes per source row
     const int tpw = 32 / NX4;                                  // tasks per warp pass
     const int sub = lane / NX4, m = lane - sub * NX4;
     const bool lane_on = sub < tpw;
@@ -254,6 +265,25 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
           const int r = task / p.ncg, cg = task - r * p.ncg;
           const int sy = (bd.r0 + r) * p.cs + cy - p.p0y;
           const bool rowok = (unsigned)sy < (unsigned)p.SH;
+          if (!FIRST && p.scalar_w) {
+            // narrow planes whose rows are not 16-byte multiples (GRUModel's 10x10 and 5x5 layers):
+            // lane m handles pixel x = m of 4 channels with scalar loads; consecutive lanes store
+            // consecutive 16-byte units (conflict-free)
+            float c4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const long long a = (long long)bd.img * p.C * plane + (long long)(cg * 4 + c) * plane + sy * p.SW + m;
+              float v = rowok ? __ldg(p.src + a) : 0.0f;
+              if (rowok && p.mask) v = __ldg(p.mask + a) > 0.f ? v : 0.f;
+              c4[c] = v;
+            }
+            const int xq = m + p.p0x;
+            uint8_t* d = buf + ((size_t)cg * p.plane_pos + r * p.PW) * 16;
+            if (p.cs == 1) d += (size_t)(p.cls_pos[0] + xq) * 16;
+            else d += (size_t)(p.cls_pos[cy * 2 + (xq & 1)] + (xq >> 1)) * 16;
+            store_split(d, p.half_bytes, c4[0], c4[1], c4[2], c4[3]);
+            continue;
+          }
           float4 v0, v1, v2, v3;
           int e0 = 0, pl4 = 0;
           if constexpr (FIRST) {
@@ -322,13 +352,14 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
     // its operands go through vector registers; the loop below lives entirely in uniform
     // registers (about 3 instructions per MMA) and tiles are dealt round-robin to SH_NISS warps.
     const uint32_t me = (uint32_t)(warp - SH_MMA);
-    constexpr uint32_t idesc = make_idesc(NPAD);
+    const uint32_t niss = nslot < (uint32_t)SH_NISS ? nslot : (uint32_t)SH_NISS;   // active issuer warps
+    constexpr uint32_t idesc1 = make_idesc(NPAD);             // X_lo * W_hi
+    constexpr uint32_t idesc2 = make_idesc(NACC);             // X_hi * [W_hi | W_lo]
     constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);    // SBO = 128 B, descriptor version 1
     const uint32_t a_w0 = (uint32_t)make_desc_nosw(smem_u32(bufs), (uint32_t)p.plane_pos * 16u, 128);
-    const uint32_t b_w0 = (uint32_t)make_desc_nosw(smem_u32(wsm), NPAD * 16, 128);
+    const uint32_t b_w0 = (uint32_t)make_desc_nosw(smem_u32(wsm), NACC * 16, 128);
     // 32-bit arithmetic on the low descriptor word only (address >> 4 in bits 0-13, no carry out)
     const uint32_t buf16 = (uint32_t)p.buf_bytes >> 4, half16 = (uint32_t)p.half_bytes >> 4;
-    const uint32_t wlo16 = (uint32_t)p.w_half_bytes >> 4;
     const uint32_t kstep16 = 2u * (uint32_t)p.plane_pos;      // 8 channels = 2 channel-group planes
     StageRing ring(p.nbuf);
     uint32_t tcount = 0, slot = 0, sphase = 0;
@@ -342,25 +373,25 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
         for (int t = 0; t < bd.ntile; ++t, ++tcount) {
           const uint32_t ab = slot, aphase = sphase;
           if (++slot == nslot) { slot = 0; sphase ^= 1u; }
-          if ((tcount & (SH_NISS - 1)) != me) continue;
+          // An accumulator slot must always be (re)used by the SAME issuer warp: its wait on
+          // acc_empty is a parity wait, which cannot tell "two phases behind" from "done", so a
+          // warp may only ever be one use ahead of the drain -- true when tile i goes to warp
+          // i % niss with niss dividing into the slot rotation (niss = min(SH_NISS, nslot)).
+          if ((tcount & (niss - 1)) != me) continue;
           mbar_wait(&acc_empty[ab], aphase ^ 1u);
           tc_fence_after();
           if (!(p.dbg & 2) && elect_one()) {
             int g = p.oc[oc].tap0;
             for (int ch = 0; ch < p.nch; ++ch) {
-              const uint32_t tmem_d = tmem_base + (ab * p.nch + ch) * NPAD;
+              const uint32_t tmem_d = tmem_base + (ab * p.nch + ch) * NACC;
               uint32_t acc = 0;
               for (int tp = 0; tp < tpc; ++tp, ++g) {
                 uint32_t a_hi = a_buf + p.taps[g].a_off16 + (uint32_t)(t * TM);
                 uint32_t b_hi = b_w0 + (uint32_t)(g * p.ksteps) * (WBLK >> 4);
                 for (int ks = 0; ks < p.ksteps; ++ks) {
-                  if (!FIRST || p.nsplit == 2) {
-                    mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + half16, b_hi, acc);
-                    mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi, b_hi + wlo16, 1u);
-                  } else {
-                    mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi, b_hi + wlo16, acc);
-                  }
-                  mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi, b_hi, 1u);
+                  mma_tf32_imm<idesc2, DESC_HI>(tmem_d, a_hi, b_hi, acc);
+                  // ({0,1} ring sources are exact in TF32: no X_lo term)
+                  if (!FIRST || p.nsplit == 2) mma_tf32_imm<idesc1, DESC_HI>(tmem_d, a_hi + half16, b_hi, 1u);
                   acc = 1u;
                   a_hi += kstep16;
                   b_hi += (WBLK >> 4);
@@ -387,38 +418,60 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
     const int q128 = TM / p.PW, r128 = TM - q128 * p.PW;     // position step of one tile in (row, col)
     const int jr0 = row / p.PW, i0 = row - jr0 * p.PW;
     uint32_t slot = 0, sphase = 0;
+    float bsum[MASKOUT ? NCOL : 1];
+#pragma unroll
+    for (int jj = 0; jj < (MASKOUT ? NCOL : 1); ++jj) bsum[jj] = 0.0f;
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const BandInfo bd = band_info(p, item);
       float* oimg = p.out + ((long long)bd.img * p.J + p.n0 + col0) * plane;
+      const float* mimg = MASKOUT ? p.omask + ((long long)bd.img * p.J + p.n0 + col0) * plane : nullptr;
       for (int oc = 0; oc < p.noc; ++oc) {
         const ShiftClass c = p.oc[oc];
         int jr = jr0, i = i0;
         for (int t = 0; t < bd.ntile; ++t) {
           const uint32_t ab = slot;
+          // position of this lane's accumulator row; the mask values of its NCOL channels are
+          // requested BEFORE the wait on the accumulator so their latency hides behind the MMAs
+          const int j = bd.r0 + jr;
+          const bool pvalid = jr < bd.rows && j < c.qh && i < c.qw && !(p.dbg & 8);
+          const int idx0 = (j * p.os + c.a) * p.OutW + i * p.os + c.b;
+          float mk[MASKOUT ? NCOL : 1];
+          if constexpr (MASKOUT) {
+#pragma unroll
+            for (int jj = 0; jj < NCOL; ++jj)
+              mk[jj] = (pvalid && jj < nvalid) ? __ldg(mimg + idx0 + jj * plane) : 0.0f;
+          }
           mbar_wait(&acc_full[ab], sphase);
           if (++slot == nslot) { slot = 0; sphase ^= 1u; }
           tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.nch * NPAD + col0;
+          // chain ch: columns [ch*NACC, +NPAD) hold x*w_hi (both x terms), [ch*NACC + NPAD, +NPAD) x_hi*w_lo
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.nch * NACC + col0;
           float acc[NCOL];
           if (NCOL <= 16 && p.nch == 3) {
-            // all three chains in flight, one wait
+            // three chains in flight per wait: first the main halves, then the w_lo halves
             uint32_t r0[NCOL], r1[NCOL], r2[NCOL];
-            tmem_ld<LDN>(taddr, r0);
-            tmem_ld<LDN>(taddr + NPAD, r1);
-            tmem_ld<LDN>(taddr + 2 * NPAD, r2);
-            if (NCOL > LDN) {
-              tmem_ld<LDN>(taddr + LDN, r0 + NCOL - LDN);
-              tmem_ld<LDN>(taddr + NPAD + LDN, r1 + NCOL - LDN);
-              tmem_ld<LDN>(taddr + 2 * NPAD + LDN, r2 + NCOL - LDN);
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int jj = 0; jj < NCOL; ++jj)
-              acc[jj] = (__uint_as_float(r0[jj]) + __uint_as_float(r1[jj])) + __uint_as_float(r2[jj]);
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t ta = taddr + half * NPAD;
+              tmem_ld<LDN>(ta, r0);
+              tmem_ld<LDN>(ta + NACC, r1);
+              tmem_ld<LDN>(ta + 2 * NACC, r2);
+              if (NCOL > LDN) {
+                tmem_ld<LDN>(ta + LDN, r0 + NCOL - LDN);
+                tmem_ld<LDN>(ta + NACC + LDN, r1 + NCOL - LDN);
+                tmem_ld<LDN>(ta + 2 * NACC + LDN, r2 + NCOL - LDN);
+              }
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int jj = 0; jj < NCOL; ++jj) {
+                const float t = (__uint_as_float(r0[jj]) + __uint_as_float(r1[jj])) + __uint_as_float(r2[jj]);
+                acc[jj] = half ? acc[jj] + t : t;
+              }
+            }
           } else {
 #pragma unroll
             for (int jj = 0; jj < NCOL; ++jj) acc[jj] = 0.0f;
-            for (int ch = 0; ch < p.nch; ++ch) {
+            for (int ch = 0; ch < 2 * p.nch; ++ch) {          // (chain, half) pairs: NPAD columns apart
               uint32_t r[NCOL];
 #pragma unroll
               for (int c0 = 0; c0 < NCOL; c0 += LDN) tmem_ld<LDN>(taddr + ch * NPAD + (uint32_t)c0, r + c0);
@@ -430,22 +483,38 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[ab]);
-          const int j = bd.r0 + jr;
-          if (jr < bd.rows && j < c.qh && i < c.qw && !(p.dbg & 8)) {
-            int idx = (j * p.os + c.a) * p.OutW + i * p.os + c.b;
+          if (pvalid) {
+            int idx = idx0;
 #pragma unroll
             for (int j4 = 0; j4 < NCOL / 4; ++j4) {
               const float4 b4 = bias4[j4];
               const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
-                if (j4 * 4 + u < nvalid) oimg[idx] = fmaxf(acc[j4 * 4 + u] + bb[u], floor_v);
+                if (j4 * 4 + u < nvalid) {
+                  float v = fmaxf(acc[j4 * 4 + u] + bb[u], floor_v);
+                  if constexpr (MASKOUT) {
+                    v = mk[j4 * 4 + u] > 0.0f ? v : 0.0f;
+                    bsum[j4 * 4 + u] += v;
+                  }
+                  oimg[idx] = v;
+                }
                 idx += plane;
               }
             }
           }
           jr += q128; i += r128;
           if (i >= p.PW) { i -= p.PW; ++jr; }
+        }
+      }
+    }
+    if constexpr (MASKOUT) {
+      // per-thread fp32 running sums (a few thousand terms each) -> warp sum -> one f64 atomic per channel
+      if (p.obias) {
+#pragma unroll
+        for (int jj = 0; jj < NCOL; ++jj) {
+          const float t = warp_sum(bsum[jj]);
+          if (lane == 0 && jj < nvalid) atomicAdd(p.obias + p.n0 + col0 + jj, (double)t);
         }
       }
     }
@@ -498,14 +567,10 @@ static bool shift_plan(ShiftParams* p, int npad) {
   return false;
 }
 
-template <int NPAD, bool FIRST = false>
+template <int NPAD, bool FIRST = false, bool MASKOUT = false>
 static int shift_launch(ShiftParams& p, cudaStream_t st) {
-  auto kern = conv_shift_kernel<NPAD, FIRST>;
-  static bool configured = false;
-  if (!configured) {
-    A2C_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_LIMIT));
-    configured = true;
-  }
+  auto kern = conv_shift_kernel<NPAD, FIRST, MASKOUT>;
+  A2C_CUDA_CHECK(set_max_dynamic_smem(reinterpret_cast<const void*>(kern), SH_SMEM_LIMIT));
   const int nitems = p.N * p.nbands;
   int grid = num_sms();
   if (grid > nitems) grid = nitems;
@@ -522,7 +587,7 @@ static int floordiv_i(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b
 using tc::ShiftParams;
 
 static bool shift_enabled() {
-  static const bool off = getenv("A2C_NO_SHIFT") != nullptr;
+  static const bool off = debug_knob("A2C_NO_SHIFT") != 0;
   return !off;
 }
 
@@ -534,17 +599,21 @@ static int shift_run(ShiftParams& p, FillTaps fill, cudaStream_t st) {
   for (int ci = 0; ci < 3; ++ci) {
     const int npad = cands[ci];
     if (npad >= 2 * p.J && npad > 16) continue;                 // do not pad a narrow layer to a wide tile
-    if (2 * p.nch * npad > 512) continue;                       // TMEM columns
+    if (p.omask && npad == 64) continue;                        // masked epilogue: 16 / 32 wide only
+    if (2 * p.nch * 2 * npad > 512) continue;                   // TMEM columns: 2 slots x nch chains x (hi | lo) halves
     if ((long long)p.ntaps_total * p.ksteps * npad * 64 > 80 * 1024 && npad > 16) continue;
     if (!tc::shift_plan(&p, npad)) continue;
     if (!fill(p)) return 1;
-    { const char* e = getenv("A2C_SHIFT_DBG"); p.dbg = e ? atoi(e) : 0; }
+    p.dbg = debug_knob("A2C_SHIFT_DBG");
     for (int n0 = 0; n0 < p.J; n0 += npad) {
       p.n0 = n0;
       int rc;
       if (p.cvalid < p.C) {
         if (npad == 64) return 1;                                 // first layers: 16 / 32 wide only
         rc = npad == 32 ? tc::shift_launch<32, true>(p, st) : tc::shift_launch<16, true>(p, st);
+      } else if (p.omask) {
+        if (npad == 64) return 1;                                 // masked epilogue: up to 32 channels per pass
+        rc = npad == 32 ? tc::shift_launch<32, false, true>(p, st) : tc::shift_launch<16, false, true>(p, st);
       } else {
         rc = npad == 64 ? tc::shift_launch<64>(p, st) : npad == 32 ? tc::shift_launch<32>(p, st)
                                                                    : tc::shift_launch<16>(p, st);
@@ -580,7 +649,12 @@ int conv_fwd_shift_try(const float* X, const a2c_state_view* xview, const float*
   p.cs = S; p.p0y = P; p.p0x = P;
   p.PW = s->OW + (K - 1) / S;
   for (int cy = 0; cy < S; ++cy) p.rext_y[cy] = (K - 1 - cy) / S;
-  if ((s->W & 3) || s->W > 128 || (!xview && (reinterpret_cast<uintptr_t>(X) & 15))) return 1;
+  if (s->W & 3) {
+    if (first || s->W > 32) return 1;
+    p.scalar_w = 1;
+  } else if (s->W > 128 || (!xview && (reinterpret_cast<uintptr_t>(X) & 15))) {
+    return 1;
+  }
   p.QH = s->OH; p.noc = 1; p.os = 1;
   p.oc[0] = {0, K * K, 0, 0, s->OH, s->OW};
   p.ntaps_total = K * K; p.nch = K;                 // one accumulator chain per kernel row
@@ -601,13 +675,16 @@ bool conv_dgrad_shift_ok(const a2c_conv_shape* s) {
   const int S = s->stride;
   if (!shift_enabled() || s->K != 3 || s->pad != 1 || (S != 1 && S != 2) || (s->Cout % 8) != 0) return false;
   if ((S == 2 && ((s->H | s->W) & 1)) || s->Cin > 128) return false;
-  return (s->OW & 3) == 0 && s->OW <= 128;
+  return (s->OW & 3) == 0 ? s->OW <= 128 : s->OW <= 32;     // narrow odd planes: scalar producers
 }
 
-int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
-                         const a2c_conv_shape* s, cudaStream_t st) {
+// Xmask / dbias_prev (both optional): dX = Xmask > 0 ? dX : 0 and dbias_prev f64 [Cin] += per-channel sums
+// of the masked dX (the caller zeroes it) -- the ReLU + bias gradient of the layer that produced X.
+int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, float* dX, const float* Xmask,
+                         double* dbias_prev, int N, const a2c_conv_shape* s, cudaStream_t st) {
   const int K = s->K, S = s->stride, P = s->pad;
   if (!conv_dgrad_shift_ok(s)) return 1;
+  if (dbias_prev && !Xmask) return 1;
   static thread_local ShiftParams p;
   memset(&p, 0, sizeof(p));
   p.src = dY; p.mask = Ymask; p.N = N; p.C = s->Cout; p.SH = s->OH; p.SW = s->OW;
@@ -626,13 +703,16 @@ int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, f
   p.p0y = -dmin; p.p0x = -dmin;
   p.rext_y[0] = dmax - dmin;
   p.PW = cdiv(s->W, S) + p.rext_y[0];
-  if ((s->OW & 3) || s->OW > 128 || (reinterpret_cast<uintptr_t>(dY) & 15) ||
-      (Ymask && (reinterpret_cast<uintptr_t>(Ymask) & 15)))
+  if (s->OW & 3) {
+    p.scalar_w = 1;
+  } else if ((reinterpret_cast<uintptr_t>(dY) & 15) || (Ymask && (reinterpret_cast<uintptr_t>(Ymask) & 15))) {
     return 1;
+  }
   p.QH = cdiv(s->H, S); p.noc = S * S; p.os = S;
   p.nch = 1;
   p.wt = Wt; p.wsn = K * K; p.wsk = s->Cin * K * K; p.J = s->Cin;
   p.out = dX; p.OutH = s->H; p.OutW = s->W;
+  p.omask = Xmask; p.obias = dbias_prev;
   p.ntaps_total = K * K;
   const int H = s->H, W = s->W;
   return shift_run(p, [K, S, P, H, W, dmin](ShiftParams& q) {

@@ -42,9 +42,15 @@ constexpr int WG_PROD = 12;
 constexpr int WG_NISS = 4;
 constexpr int WG_DRAIN0 = WG_PROD, WG_MMA = WG_DRAIN0 + NUM_EPI_WARPS, WG_ALLOC = WG_MMA + WG_NISS;
 constexpr int WG_THREADS = 32 * (WG_ALLOC + 1);
-constexpr int WG_NSLOT = 4;
+constexpr int WG_NSLOT = 2;
+constexpr int WG_NACT = WG_NSLOT < 4 ? WG_NSLOT : 4;   // issuer warps that take chunks (<= WG_NISS)
 constexpr int WG_N = 32;                     // output channels per launch
-constexpr int WG_NACC = 3 * WG_N;            // TMEM columns of one accumulator set (kx = 0, 1, 2)
+constexpr int WG_NACC = 3 * WG_N;            // accumulator values per row (kx = 0, 1, 2) in the per-CTA partials
+// TMEM columns of one accumulator set: per kx [x * dy_hi (32) | x_hi * dy_lo (32)].  The 3xTF32 product is
+// issued as two MMAs,  D[:, 0:64] (+)= X_hi * [dY_hi | dY_lo]  and  D[:, 0:32] += X_lo * dY_hi  (the dY lo
+// copy sits one LBO = o_half bytes after the hi copy, i.e. it is the second 32-slot atom along N), which
+// cuts the tensor core's shared-memory operand reads per product from 3 (A + B) to 2 A + 1.5 B.
+constexpr int WG_TCOLS = 3 * 2 * WG_N;
 constexpr int WG_ROWB = 128;                 // bytes of one position row (32 slots)
 // descriptor high word: SBO = 512 B (4 rows), version 1, base offset 0, SWIZZLE_128B_BASE32B (= 1)
 constexpr uint32_t WG_DESC_HI = (512u >> 4) | (1u << 14) | (1u << 29);
@@ -58,7 +64,9 @@ struct WgShiftParams {
   int nsplit;            // 2: X has a lo part (3 MMAs per product), 1: X exact in TF32 (2 MMAs)
   const float* dy;       // f32 [N][Cout][OH][OW]
   const float* mask;     // optional (layer output Y): dY counts only where mask > 0
-  int N, Cin, H, W, Cout, OH, OW;
+  int N, Cin, H, W, Cout, OH, OW;   // Cin: input channels of THIS launch (a chunk of <= 32 of CinTot)
+  int CinTot, ci0;       // channels per image of x, first channel of this launch
+  int scalar_w;          // W or OW not a multiple of 4 (10x10 / 5x5 planes): one pixel per lane, scalar loads
   int S;                 // stride
   int pack2;             // stride 1, Cin <= 16: slots [16,32) = channels of the next image row
   int ncx;               // x-parity planes per X row (1, or 2 for stride 2)
@@ -103,6 +111,13 @@ __device__ __forceinline__ void wg_tmem_ld16(uint32_t taddr, uint32_t* r) {
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ void wg_tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
       : "r"(taddr));
 }
 
@@ -248,7 +263,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
           const int sy = it.r0 + r - 1;
           const int x4 = 4 * (g0 + gi);
           const bool ok = (unsigned)sy < (unsigned)p.H && (unsigned)x4 < (unsigned)p.W;
-          float px[4][4];
+          // Lane gi holds a 4 pixel x 4 channel block.  In step (jj, kk) it stores pixel
+          // (jj + gi) & 3 into chunk k = (kk + (gi >> 2)) % 3 of row r - k: the 8 lanes of a
+          // quarter-warp (4 consecutive gi at one k, the next 4 at k + 1) then hit 4 swizzle
+          // phases x 2 chunk parities = 8 different 16-byte bank groups (2-way only when the two
+          // k's are 2 and 0).  With every lane on the same (pixel, k) all 8 stores of a
+          // quarter-warp landed in one bank group (ncu r1: 70 % of this kernel's shared
+          // wavefronts were conflicts).
+          float4 vc[4];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -261,27 +283,72 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
                 v = __ldg(reinterpret_cast<const float4*>(p.x + a));
               }
             }
-            px[0][c] = v.x; px[1][c] = v.y; px[2][c] = v.z; px[3][c] = v.w;
+            vc[c] = rot4(v, gi);
           }
+          const float px[4][4] = {{vc[0].x, vc[1].x, vc[2].x, vc[3].x}, {vc[0].y, vc[1].y, vc[2].y, vc[3].y},
+                                  {vc[0].z, vc[1].z, vc[2].z, vc[3].z}, {vc[0].w, vc[1].w, vc[2].w, vc[3].w}};
+          const int krot = gi >> 2;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int xp = x4 + j - xs;
-            if (xp < 0 || x4 + j >= xe) continue;
+          for (int kk = 0; kk < 3; ++kk) {
+            int k = kk + krot;
+            k -= 3 * (k / 3);
+            if (r - k < 0) continue;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              if (r - k < 0) continue;
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = (jj + gi) & 3;
+              const int xp = x4 + j - xs;
+              if (xp < 0 || x4 + j >= xe) continue;
               const uint32_t off = (uint32_t)((r - k) * p.PWx + xp) * WG_ROWB;
-              wg_store_split(buf + off + wg_swz(buf_a + off, k), p.x_half, px[j][0], px[j][1], px[j][2], px[j][3]);
+              uint8_t* d = buf + off + wg_swz(buf_a + off, k);
+              if (p.nsplit == 2) {
+                wg_store_split(d, p.x_half, px[jj][0], px[jj][1], px[jj][2], px[jj][3]);
+              } else {
+                // {0,1} ring values are exact in TF32: the lo copy stays zero and is never read
+                *reinterpret_cast<float4*>(d) = make_float4(px[jj][0], px[jj][1], px[jj][2], px[jj][3]);
+              }
             }
           }
         }
       } else {
       // --- X band.  A lane converts 4 consecutive pixels (one float4 per channel) of 4 channels. ---
         uint8_t* buf = xb + (size_t)ring.s * p.x_buf;
-        const float4* simg = reinterpret_cast<const float4*>(p.x + (long long)it.img * p.Cin * xplane);
+        const float* ximg = p.x + ((long long)it.img * p.CinTot + p.ci0) * xplane;
+        const int nrow_s = p.S == 1 ? it.rows + 2 : 2 * it.rows + 1;
+        if (p.scalar_w) {
+          // narrow planes (rows not 16-byte multiples): lane <-> one needed source column, 4 channels,
+          // scalar loads; a task is (source row, channel group)
+          const int tpws = 32 / XN > 0 ? 32 / XN : 1;
+          const int subs = lane / XN, xp = lane - subs * XN;
+          const int col = p.S * it.c0 - 1 + xp;
+          const int ntask = nrow_s * ncgx;
+          for (int task = pw * tpws + subs; task < ntask; task += pgw * tpws) {
+            if (subs >= tpws) continue;
+            const int r = task / ncgx, cg = task - r * ncgx;
+            const int sy = p.S * it.r0 + r - 1;
+            const bool ok = (unsigned)col < (unsigned)p.W && (unsigned)sy < (unsigned)p.H;
+            float c4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              c4[c] = ok ? __ldg(ximg + (long long)(cg * 4 + c) * xplane + sy * p.W + col) : 0.0f;
+            const uint32_t pos = (uint32_t)(p.ncx * r * p.PWx + (p.S == 1 ? xp : (xp & 1) * p.PWx + (xp >> 1)));
+            const uint32_t c16 = ((uint32_t)cg & 1u) << 4, c32 = (uint32_t)cg >> 1;
+            const float4 h = make_float4(tf32_rna(c4[0]), tf32_rna(c4[1]), tf32_rna(c4[2]), tf32_rna(c4[3]));
+            const float4 l = make_float4(c4[0] - h.x, c4[1] - h.y, c4[2] - h.z, c4[3] - h.w);
+            uint8_t* d = buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16);
+            *reinterpret_cast<float4*>(d) = h;
+            *reinterpret_cast<float4*>(d + p.x_half) = l;
+            if (p.pack2 && r > 0) {
+              const uint32_t pos2 = pos - (uint32_t)p.PWx;
+              uint8_t* d2 = buf + pos2 * WG_ROWB + ((((c32 + 2u) ^ (pos2 & 3u)) << 5) | c16);
+              *reinterpret_cast<float4*>(d2) = h;
+              *reinterpret_cast<float4*>(d2 + p.x_half) = l;
+            }
+          }
+        } else {
+        const float4* simg = reinterpret_cast<const float4*>(ximg);
         const int x4 = 4 * (((p.S * it.c0) >> 2) - 1 + gix);           // first source column of this lane's group
         const bool okx = (unsigned)x4 < (unsigned)p.W;
-        const int nrow = p.S == 1 ? it.rows + 2 : 2 * it.rows + 1;     // source rows of the band
+        const int nrow = nrow_s;                                       // source rows of the band
         const int ntask = nrow * npairx;
         for (int task = pw * tpwx + subx; task < ntask; task += pgw * tpwx) {
           const int r = (task * p.inv_ncgx) >> 16, cg = 2 * (task - r * npairx) + cgpx;
@@ -317,9 +384,32 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
             }
           }
         }
+        }
       }
       // --- dY band (masked) ---
-      {
+      if (p.scalar_w) {
+        uint8_t* buf = ob + (size_t)ring.s * p.o_buf;
+        const float* dimg = p.dy + ((long long)it.img * p.Cout + p.n0) * oplane;
+        const float* mimg = p.mask ? p.mask + ((long long)it.img * p.Cout + p.n0) * oplane : nullptr;
+        const int tpws = 32 / p.OWc > 0 ? 32 / p.OWc : 1;
+        const int subs = lane / p.OWc, xo = lane - subs * p.OWc;
+        const int ntask = it.rows * p.ncgo_valid;
+        for (int task = pw * tpws + subs; task < ntask; task += pgw * tpws) {
+          if (subs >= tpws) continue;
+          const int jj = task / p.ncgo_valid, cg = task - jj * p.ncgo_valid;
+          float c4[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const long long a = (long long)(cg * 4 + c) * oplane + (it.r0 + jj) * p.OW + it.c0 + xo;
+            float v = __ldg(dimg + a);
+            if (mimg) v = __ldg(mimg + a) > 0.f ? v : 0.f;
+            c4[c] = v;
+          }
+          const uint32_t pos = (uint32_t)(jj * p.PWo + xo);
+          const uint32_t c16 = ((uint32_t)cg & 1u) << 4, c32 = (uint32_t)cg >> 1;
+          wg_store_split(buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16), p.o_half, c4[0], c4[1], c4[2], c4[3]);
+        }
+      } else {
         uint8_t* buf = ob + (size_t)ring.s * p.o_buf;
         const float4* simg = reinterpret_cast<const float4*>(p.dy + ((long long)it.img * p.Cout + p.n0) * oplane);
         const float4* mimg =
@@ -368,9 +458,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
     // descriptor low word: start address >> 4 | LBO >> 4 << 16; high word: SBO = 512 B (4 rows),
     // version 1, base offset 0, layout SWIZZLE_128B_BASE32B (= 1)
     const uint32_t a_w0 = ((smem_u32(xb) & 0x3FFFFu) >> 4) | (((uint32_t)p.a_lbo >> 4) << 16);
-    const uint32_t b_w0 = ((smem_u32(ob) & 0x3FFFFu) >> 4) | ((512u >> 4) << 16);
+    const uint32_t b_w0 = ((smem_u32(ob) & 0x3FFFFu) >> 4) | (((uint32_t)p.o_half >> 4) << 16);   // LBO: hi -> lo atom
     const uint32_t xbuf16 = (uint32_t)p.x_buf >> 4, xhalf16 = (uint32_t)p.x_half >> 4;
-    const uint32_t obuf16 = (uint32_t)p.o_buf >> 4, ohalf16 = (uint32_t)p.o_half >> 4;
+    const uint32_t obuf16 = (uint32_t)p.o_buf >> 4;
     const uint32_t xrow16 = (uint32_t)(p.S * p.ncx * p.PWx) * (WG_ROWB >> 4);   // 16-byte units per output row of X
     const uint32_t orow16 = (uint32_t)p.PWo * (WG_ROWB >> 4);
     const int ksteps = p.PWo >> 3;
@@ -384,15 +474,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
       for (int j0 = 0; j0 < it.rows; j0 += p.rpc, ++ccount) {
         const uint32_t ab = slot, aphase = sphase;
         if (++slot == WG_NSLOT) { slot = 0; sphase ^= 1u; }
-        if ((ccount & (WG_NISS - 1)) != me) continue;
+        // a slot is always reused by the same issuer warp (parity waits cannot see two phases back):
+        // chunks go to warp c % min(WG_NISS, WG_NSLOT)
+        if ((ccount & (WG_NACT - 1)) != me) continue;
         mbar_wait(&acc_empty[ab], aphase ^ 1u);
         tc_fence_after();
         if (!(p.dbg & 2) && elect_one()) {
-          const uint32_t tmem_d = tmem_base + ab * WG_NACC;
+          const uint32_t tmem_d = tmem_base + ab * WG_TCOLS;
           const int j1 = min(it.rows, j0 + p.rpc);
           // idesc / descriptor high word as immediates (uniform-register issue loop, see mma_tf32_imm)
           auto issue = [&](auto mtag) {
-            constexpr uint32_t ID = make_idesc_mn(decltype(mtag)::value, WG_N);
+            constexpr uint32_t ID1 = make_idesc_mn(decltype(mtag)::value, WG_N);        // X_lo * dY_hi
+            constexpr uint32_t ID2 = make_idesc_mn(decltype(mtag)::value, 2 * WG_N);    // X_hi * [dY_hi | dY_lo]
             uint32_t acc = 0;
             for (int jj = j0; jj < j1; ++jj) {
               uint32_t a_row = a_buf + (uint32_t)jj * xrow16;
@@ -404,13 +497,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
                   const uint32_t a_hi = a_row + (p.ncx == 1 ? (uint32_t)kx : (uint32_t)((kx & 1) * p.PWx + (kx >> 1))) * 8u;
                   // (measured: the swizzle phase comes from the absolute address bits, so a start that is
                   //  not aligned to the 512-byte pattern needs NO base offset in the descriptor)
-                  if (p.nsplit == 2) {
-                    mma_tf32_imm<ID, WG_DESC_HI>(tmem_d + kx * WG_N, a_hi + xhalf16, b_row, acc);
-                    mma_tf32_imm<ID, WG_DESC_HI>(tmem_d + kx * WG_N, a_hi, b_row + ohalf16, 1u);
-                  } else {
-                    mma_tf32_imm<ID, WG_DESC_HI>(tmem_d + kx * WG_N, a_hi, b_row + ohalf16, acc);
-                  }
-                  mma_tf32_imm<ID, WG_DESC_HI>(tmem_d + kx * WG_N, a_hi, b_row, 1u);
+                  mma_tf32_imm<ID2, WG_DESC_HI>(tmem_d + kx * 2 * WG_N, a_hi, b_row, acc);
+                  // ({0,1} ring sources are exact in TF32: no X_lo term)
+                  if (p.nsplit == 2) mma_tf32_imm<ID1, WG_DESC_HI>(tmem_d + kx * 2 * WG_N, a_hi + xhalf16, b_row, 1u);
                 }
                 acc = 1u;
                 a_row += 8 * 8;
@@ -440,14 +529,19 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         mbar_wait(&acc_full[ab], sphase);
         if (++slot == WG_NSLOT) { slot = 0; sphase ^= 1u; }
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * WG_NACC + hsel * NC;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * WG_TCOLS;
 #pragma unroll
-        for (int c0 = 0; c0 < NC; c0 += 16) {
-          uint32_t r[16];
-          wg_tmem_ld16(taddr + (uint32_t)c0, r);
+        for (int c0 = 0; c0 < NC; c0 += 8) {
+          // output (kx, co) = hsel * NC + c0 + j  lives in TMEM columns kx * 64 + co (and + 32 for the dy_lo
+          // half); 8 columns at a time keeps the 48 running sums + both halves inside the register budget
+          const int o = hsel * NC + c0;
+          const uint32_t col = (uint32_t)((o / WG_N) * 2 * WG_N + (o % WG_N));
+          uint32_t r[8], r2[8];
+          wg_tmem_ld8(taddr + col, r);
+          wg_tmem_ld8(taddr + col + WG_N, r2);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+          for (int j = 0; j < 8; ++j) acc[c0 + j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
         }
         tc_fence_before();
         __syncwarp();
@@ -470,8 +564,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
 //   first layer (Cin <= 4) : ky * 4 + ci     packed (stride 1, Cin <= 16) : ky * 16 + ci     otherwise : ky * 32 + ci
 // M = 64 accumulators live in TMEM lanes (m % 16) + 32 * (m / 16).
 __global__ void __launch_bounds__(256)
-wg_shift_reduce_kernel(const float* __restrict__ partial, int grid, int pack, int mrows, int Cin, int Cout,
-                       int n0, float* __restrict__ dW, int bias_row, float* __restrict__ dbias) {
+wg_shift_reduce_kernel(const float* __restrict__ partial, int grid, int pack, int mrows, int Cin, int CinTot,
+                       int ci0, int Cout, int n0, float* __restrict__ dW, int bias_row, float* __restrict__ dbias) {
   const int nco = min(WG_N, Cout - n0);
   const int nw = nco * Cin * 9;
   const int total = nw + (dbias && bias_row >= 0 ? nco : 0);
@@ -488,7 +582,7 @@ wg_shift_reduce_kernel(const float* __restrict__ partial, int grid, int pack, in
     for (int b = 0; b < grid; ++b)
       s += (double)partial[((size_t)b * 128 + lane_row) * WG_NACC + kx * WG_N + co];
     if (is_bias) dbias[n0 + co] = (float)s;
-    else dW[(((size_t)(n0 + co) * Cin + ci) * 3 + ky) * 3 + kx] = (float)s;
+    else dW[(((size_t)(n0 + co) * CinTot + ci0 + ci) * 3 + ky) * 3 + kx] = (float)s;
   }
 }
 
@@ -512,6 +606,23 @@ wg_bias_sum_kernel(const float* __restrict__ dY, const float* __restrict__ mask,
       t = (v.x + v.y) + (v.z + v.w);
     }
     s += (double)t;
+  }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) atomicAdd(&acc[c], s);
+}
+// same for planes whose size is not a multiple of 4 (5x5)
+__global__ void __launch_bounds__(256)
+wg_bias_sum_scalar_kernel(const float* __restrict__ dY, const float* __restrict__ mask, double* __restrict__ acc,
+                          int N, int C, int HW) {
+  __shared__ double scratch[32];
+  const int c = blockIdx.y;
+  double s = 0.0;
+  const long long per = (long long)N * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW);
+    const long long a = ((long long)n * C + c) * HW + (i - (long long)n * HW);
+    const float v = __ldg(dY + a);
+    s += (double)((!mask || __ldg(mask + a) > 0.f) ? v : 0.f);
   }
   s = block_sum(s, scratch);
   if (threadIdx.x == 0) atomicAdd(&acc[c], s);
@@ -546,7 +657,7 @@ static bool wg_plan(WgShiftParams* p) {
 }  // namespace tc
 
 static bool wg_shift_enabled() {
-  static const bool off = getenv("A2C_NO_SHIFT") != nullptr || getenv("A2C_NO_SHIFT_WGRAD") != nullptr;
+  static const bool off = debug_knob("A2C_NO_SHIFT") != 0 || debug_knob("A2C_NO_SHIFT_WGRAD") != 0;
   return !off;
 }
 
@@ -554,14 +665,31 @@ long long conv_wgrad_shift_workspace(const a2c_conv_shape* s) {
   return (long long)num_sms() * 128 * tc::WG_NACC * 4 + (long long)(s ? s->Cout + 2 : 2) * 8 + 256;
 }
 
+// Output columns per chunk; 0 when the row cannot be tiled.  Planes whose rows are 16-byte multiples
+// use the float4 producers (chunks of <= 40 / 20 positions, multiple of 4); narrow odd planes (10x10,
+// 5x5: GRUModel's tail) use the scalar producers, whose chunk and halo must fit one warp.
+static int wg_chunk_cols(const a2c_conv_shape* s, bool* scalar) {
+  const int S = s->stride;
+  *scalar = ((s->W | s->OW) & 3) != 0;
+  if (*scalar) {
+    const int owc = s->OW;                                   // one chunk
+    const int xn = S == 1 ? owc + 2 : 2 * owc + 1;
+    return (owc <= 32 && xn <= 32) ? owc : 0;
+  }
+  const int ncol = cdiv(s->OW, S == 1 ? 40 : 20);
+  if (s->OW % ncol || ((s->OW / ncol) & 3)) return 0;
+  return s->OW / ncol;
+}
+
 bool conv_wgrad_shift_ok(const a2c_conv_shape* s) {
   const int S = s->stride;
   if (!wg_shift_enabled() || s->K != 3 || s->pad != 1 || (S != 1 && S != 2)) return false;
   const bool first = s->Cin <= 4 && S == 1;
-  if ((!first && (s->Cin & 3)) || (s->Cout & 3) || s->Cin > 32 || (s->W & 3) || (s->OW & 3)) return false;
+  if ((!first && (s->Cin & 3)) || (s->Cout & 3)) return false;
   if (S == 2 && ((s->H | s->W) & 1)) return false;
-  const int ncol = cdiv(s->OW, S == 1 ? 40 : 20);
-  return s->OW % ncol == 0 && ((s->OW / ncol) & 3) == 0;
+  bool scalar;
+  if (wg_chunk_cols(s, &scalar) == 0) return false;
+  return !(first && scalar);
 }
 
 // 0 = ran, 1 = not supported (caller falls back), else error
@@ -577,23 +705,29 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
         ((xview->stride_r | xview->stride_t | xview->stride_c) & 3))
       return 1;
   }
-  if ((X && (reinterpret_cast<uintptr_t>(X) & 15)) || (reinterpret_cast<uintptr_t>(dY) & 15) ||
-      (Ymask && (reinterpret_cast<uintptr_t>(Ymask) & 15)))
+  bool scalar;
+  const int owc = wg_chunk_cols(s, &scalar);
+  if (!scalar && ((X && (reinterpret_cast<uintptr_t>(X) & 15)) || (reinterpret_cast<uintptr_t>(dY) & 15) ||
+                  (Ymask && (reinterpret_cast<uintptr_t>(Ymask) & 15))))
     return 1;
   if (workspace_bytes < conv_wgrad_shift_workspace(s)) return 1;
+  double* bias_acc = reinterpret_cast<double*>(workspace);
+  bool bias_done = dbias == nullptr;
+  int grid = num_sms();
+  // input channels in chunks of 32 (the channel slots of one 128-byte position row)
+  for (int ci0 = 0; ci0 < s->Cin; ci0 += 32) {
+  const int cin = s->Cin - ci0 < 32 ? s->Cin - ci0 : 32;
   static thread_local tc::WgShiftParams p;
   memset(&p, 0, sizeof(p));
-  p.x = xview ? nullptr : X; p.dy = dY; p.mask = Ymask; p.N = N; p.Cin = s->Cin; p.H = s->H; p.W = s->W;
+  p.x = xview ? nullptr : X; p.dy = dY; p.mask = Ymask; p.N = N; p.Cin = cin; p.H = s->H; p.W = s->W;
+  p.CinTot = s->Cin; p.ci0 = ci0; p.scalar_w = scalar ? 1 : 0;
   if (xview) { p.view = *xview; p.use_view = 1; }
   p.pack3 = first ? 1 : 0;
-  { const int np = first ? 1 : (s->Cin / 4 + 1) / 2; p.inv_ncgx = (65536 + np - 1) / np; }
+  { const int np = first ? 1 : (cin / 4 + 1) / 2; p.inv_ncgx = (65536 + np - 1) / np; }
   p.nsplit = xview ? 1 : 2;
   p.Cout = s->Cout; p.OH = s->OH; p.OW = s->OW; p.S = S; p.ncx = S;
-  // column chunks of at most 40 (stride 2: 20) output positions (multiple of 4) that tile the row exactly
-  p.ncol = cdiv(s->OW, S == 1 ? 40 : 20);
-  if (s->OW % p.ncol) return 1;
-  p.OWc = s->OW / p.ncol;
-  if (p.OWc & 3) return 1;
+  p.OWc = owc;
+  p.ncol = s->OW / owc;
   p.PWx = S == 1 ? p.OWc + 2 : p.OWc + 1;
   p.PWo = (p.OWc + 7) & ~7;
   p.pack2 = (S == 1 && s->Cin <= 16 && !first) ? 1 : 0;
@@ -601,40 +735,35 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   p.a_lbo = (p.pack2 ? 2 : 1) * p.ncx * p.PWx * tc::WG_ROWB;     // one (packed: two) source rows
   if (p.a_lbo >= (1 << 18)) return 1;
   if (!tc::wg_plan(&p)) return 1;
-  // rows per accumulator chunk: a TMEM chain of at most ~64 MMAs (3 per k-step)
+  // rows per accumulator chunk: a TMEM chain of at most ~64 MMAs (2-3 per k-step)
   const int ksteps = p.PWo / 8;
   p.rpc = 20 / ksteps;
-  if (p.rpc > p.Rb / tc::WG_NISS) p.rpc = p.Rb / tc::WG_NISS;   // and every issuer warp gets a share of each band
+  if (p.rpc > p.Rb / tc::WG_NACT) p.rpc = p.Rb / tc::WG_NACT;   // and every active issuer warp gets a share of each band
   if (p.rpc < 1) p.rpc = 1;
   {
     // two producer groups when half of the warps finish a band's X and dY tasks in one pass
     const int half = tc::WG_PROD / 2;
-    const int ngx = S == 1 ? p.OWc / 4 + 2 : p.OWc / 2 + 1, ngo = p.OWc / 4;
+    const int ngx = S == 1 ? p.OWc / 4 + 2 : p.OWc / 2 + 1, ngo = p.OWc / 4 > 0 ? p.OWc / 4 : 1;
     const int tpwx = first ? (32 / ngx > 0 ? 32 / ngx : 1) : (32 / (2 * ngx) > 0 ? 32 / (2 * ngx) : 1);
     const int ncgo = (s->Cout < tc::WG_N ? s->Cout : tc::WG_N) / 4;
     p.pair_o = ncgo > 4 ? 1 : 0;
     const int lpo = p.pair_o ? 2 * ngo : ngo;
     const int tpwo = 32 / lpo > 0 ? 32 / lpo : 1;
-    const int xtasks = first ? p.Rb + 2 : p.xrows * ((s->Cin / 4 + 1) / 2);
+    const int xtasks = first ? p.Rb + 2 : p.xrows * ((cin / 4 + 1) / 2);
     const int otasks = p.Rb * (p.pair_o ? (ncgo + 1) / 2 : ncgo);
-    p.pgroups = (xtasks <= half * tpwx && otasks <= half * tpwo) ? 2 : 1;
-    if (getenv("A2C_WG_PGROUPS")) p.pgroups = atoi(getenv("A2C_WG_PGROUPS")) == 2 ? 2 : 1;
+    p.pgroups = (!scalar && xtasks <= half * tpwx && otasks <= half * tpwo) ? 2 : 1;
+    if (const int k = debug_knob("A2C_WG_PGROUPS")) p.pgroups = k == 2 ? 2 : 1;
   }
   // bias gradient from the MMA when the X rows have a free 4-slot chunk (first layers: chunk 3 of the
-  // packed atom; 20- and 24-channel layers: chunk Cin / 4); otherwise the separate masked sum below
-  p.ones_chunk = first ? 3 : ((!p.pack2 && s->Cin <= 28) ? s->Cin / 4 : -1);
+  // packed atom; chunks of 20..28 channels: chunk cin / 4); otherwise the separate masked sum below
+  p.ones_chunk = bias_done ? -1 : (first ? 3 : ((!p.pack2 && cin <= 28) ? cin / 4 : -1));
   const int bias_row = p.ones_chunk >= 0 ? 4 * p.ones_chunk : -1;     // accumulator row (ky = 0 atom)
-  double* bias_acc = reinterpret_cast<double*>(workspace);
   p.partial = reinterpret_cast<float*>(bias_acc + ((s->Cout + 1) & ~1));
-  { const char* e = getenv("A2C_WG_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.dbg = debug_knob("A2C_WG_DBG");
   auto kern = tc::conv_shift_wgrad_kernel;
-  static bool configured = false;
-  if (!configured) {
-    A2C_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WG_SMEM_LIMIT));
-    configured = true;
-  }
-  int grid = num_sms();
+  A2C_CUDA_CHECK(set_max_dynamic_smem(reinterpret_cast<const void*>(kern), tc::WG_SMEM_LIMIT));
   const int items = N * p.nbands * p.ncol;
+  grid = num_sms();
   if (grid > items) grid = items;
   for (int n0 = 0; n0 < s->Cout; n0 += tc::WG_N) {
     p.n0 = n0;
@@ -644,18 +773,30 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
     g_launches++;
     A2C_LAUNCH_CHECK();
     const int nco = s->Cout - n0 < tc::WG_N ? s->Cout - n0 : tc::WG_N;
-    tc::wg_shift_reduce_kernel<<<cdiv(nco * s->Cin * 9 + nco, 256), 256, 0, st>>>(
-        p.partial, grid, p.pack3 ? 3 : (p.pack2 ? 2 : 0), p.mrows, s->Cin, s->Cout, n0, dW, bias_row, dbias);
+    tc::wg_shift_reduce_kernel<<<cdiv(nco * cin * 9 + nco, 256), 256, 0, st>>>(
+        p.partial, grid, p.pack3 ? 3 : (p.pack2 ? 2 : 0), p.mrows, cin, s->Cin, ci0, s->Cout, n0, dW, bias_row,
+        bias_row >= 0 ? dbias : nullptr);
     g_launches++;
     A2C_LAUNCH_CHECK();
   }
-  if (dbias && bias_row < 0) {
+  if (bias_row >= 0) bias_done = true;
+  }
+  if (!bias_done) {
     A2C_CUDA_CHECK(cudaMemsetAsync(bias_acc, 0, sizeof(double) * s->Cout, st));
-    const int hw4 = s->OH * s->OW / 4;
-    int bx = (int)cdivll((long long)N * hw4, 256 * 4);
-    if (bx > 128) bx = 128;
-    if (bx < 1) bx = 1;
-    tc::wg_bias_sum_kernel<<<dim3(bx, s->Cout), 256, 0, st>>>(dY, Ymask, bias_acc, N, s->Cout, hw4);
+    if (((s->OH * s->OW) & 3) == 0 && (reinterpret_cast<uintptr_t>(dY) & 15) == 0 &&
+        (!Ymask || (reinterpret_cast<uintptr_t>(Ymask) & 15) == 0)) {
+      const int hw4 = s->OH * s->OW / 4;
+      int bx = (int)cdivll((long long)N * hw4, 256 * 4);
+      if (bx > 128) bx = 128;
+      if (bx < 1) bx = 1;
+      tc::wg_bias_sum_kernel<<<dim3(bx, s->Cout), 256, 0, st>>>(dY, Ymask, bias_acc, N, s->Cout, hw4);
+    } else {
+      int bx = (int)cdivll((long long)N * s->OH * s->OW, 256 * 8);
+      if (bx > 128) bx = 128;
+      if (bx < 1) bx = 1;
+      tc::wg_bias_sum_scalar_kernel<<<dim3(bx, s->Cout), 256, 0, st>>>(dY, Ymask, bias_acc, N, s->Cout,
+                                                                       s->OH * s->OW);
+    }
     tc::wg_bias_finish_kernel<<<cdiv(s->Cout, 64), 64, 0, st>>>(bias_acc, dbias, s->Cout);
     g_launches += 2;
     A2C_LAUNCH_CHECK();

@@ -413,11 +413,7 @@ template <int K, int S, int COT>
 static int launch_wgrad_t(ConvWgParams p, const WgPlan& pl, int wsize, float* dW, float* dbias,
                           cudaStream_t st) {
   auto kern = conv_wgrad_kernel<K, S, COT>;
-  static bool configured = false;
-  if (!configured) {
-    A2C_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  A2C_CUDA_CHECK(set_max_dynamic_smem(reinterpret_cast<const void*>(kern), 200 * 1024));
   const long long items = (long long)p.N * p.bands;
   int grid = pl.grid;
   if (items < grid) grid = (int)items;
@@ -469,8 +465,65 @@ int conv_wgrad_tc_try(const float* X, const a2c_state_view* xview, const float* 
 // conv_shift_tc.cu (3xTF32 only): 3x3 pad-1 layers as shifted-descriptor GEMMs, no im2col
 int conv_fwd_shift_try(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias, float* Y,
                        int N, const a2c_conv_shape* s, int relu, cudaStream_t st);
-int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
-                         const a2c_conv_shape* s, cudaStream_t st);
+int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, float* dX, const float* Xmask,
+                         double* dbias_prev, int N, const a2c_conv_shape* s, cudaStream_t st);
+
+// acc f64 [C] += per-channel sums of X f32 [N, C, HW] (where mask > 0, mask optional)
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const float* __restrict__ X, const float* __restrict__ mask, double* __restrict__ acc, int N,
+                   int C, int HW) {
+  __shared__ double scratch[32];
+  const int c = blockIdx.y;
+  double s = 0.0;
+  const long long per = (long long)N * HW;
+  const bool vec = (HW & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+                   (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+  if (vec) {
+    const int HW4 = HW >> 2;
+    const long long per4 = per >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per4; i += (long long)gridDim.x * blockDim.x) {
+      const int n = (int)(i / HW4);
+      const long long a = ((long long)n * C + c) * HW4 + (i - (long long)n * HW4);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(X) + a);
+      float t;
+      if (mask) {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mask) + a);
+        t = ((m.x > 0.f ? v.x : 0.f) + (m.y > 0.f ? v.y : 0.f)) + ((m.z > 0.f ? v.z : 0.f) + (m.w > 0.f ? v.w : 0.f));
+      } else {
+        t = (v.x + v.y) + (v.z + v.w);
+      }
+      s += (double)t;
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) {
+      const int n = (int)(i / HW);
+      const long long a = ((long long)n * C + c) * HW + (i - (long long)n * HW);
+      const float v = __ldg(X + a);
+      s += (double)((!mask || __ldg(mask + a) > 0.f) ? v : 0.f);
+    }
+  }
+  s = block_sum(s, scratch);
+  if (threadIdx.x == 0) atomicAdd(&acc[c], s);
+}
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
+}
+__global__ void __launch_bounds__(256)
+relu_mask_inplace_kernel(float* __restrict__ X, const float* __restrict__ M, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    if (!(M[i] > 0.0f)) X[i] = 0.0f;
+}
+
+static int channel_sum_launch(const float* X, const float* mask, double* acc, int N, int C, int HW, cudaStream_t st) {
+  int bx = (int)cdivll((long long)N * HW, 256 * 16);
+  if (bx > 128) bx = 128;
+  if (bx < 1) bx = 1;
+  channel_sum_kernel<<<dim3(bx, C), 256, 0, st>>>(X, mask, acc, N, C, HW);
+  g_launches++;
+  A2C_LAUNCH_CHECK();
+  return 0;
+}
 
 bool conv_dgrad_shift_ok(const a2c_conv_shape* s);
 bool conv_wgrad_shift_ok(const a2c_conv_shape* s);
@@ -527,7 +580,7 @@ int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, fl
   A2C_ARG_CHECK(dY && Wt && dX && N >= 0, "conv_bwd_data: bad args");
   if (N == 0) return 0;
   if (precision == 1) {
-    int rc = conv_dgrad_shift_try(dY, Ymask, Wt, dX, N, s, as_stream(stream));
+    int rc = conv_dgrad_shift_try(dY, Ymask, Wt, dX, nullptr, nullptr, N, s, as_stream(stream));
     if (rc != 1) return rc;
   }
   if (precision != 0 && !Ymask) {
@@ -547,6 +600,56 @@ int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, fl
   A2C_ARG_CHECK(p.pad >= 0, "conv_bwd_data: pad > K-1 unsupported");
   const int logicalW = (s->OW - 1) * s->stride + 1;
   return launch_fwd(p, s->K, 1, logicalW, as_stream(stream));
+}
+
+int a2c_conv2d_bwd_data_relu(const float* dY, const float* Wt, const float* X, float* dX, float* dbias_prev,
+                             int N, const a2c_conv_shape* s, int precision, void* workspace,
+                             long long workspace_bytes, void* stream) {
+  if (int rc = check_shape(s)) return rc;
+  A2C_ARG_CHECK(dY && Wt && X && dX && N >= 0, "conv_bwd_data_relu: bad args");
+  A2C_ARG_CHECK(!dbias_prev || (workspace && workspace_bytes >= (long long)sizeof(double) * s->Cin),
+                "conv_bwd_data_relu: workspace of Cin doubles needed for dbias_prev");
+  cudaStream_t st = as_stream(stream);
+  double* acc = dbias_prev ? static_cast<double*>(workspace) : nullptr;
+  if (acc) A2C_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * s->Cin, st));
+  if (N > 0) {
+    int rc = 1;
+    if (precision == 1) rc = conv_dgrad_shift_try(dY, nullptr, Wt, dX, X, acc, N, s, st);
+    if (rc != 0 && rc != 1) return rc;
+    if (rc == 1) {
+      // other paths: plain input gradient, then the mask and the channel sums as separate passes
+      if (int r2 = a2c_conv2d_bwd_data(dY, nullptr, Wt, dX, N, s, precision, stream)) return r2;
+      const long long n = (long long)N * s->Cin * s->H * s->W;
+      long long blocks = cdivll(n, 256);
+      if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+      relu_mask_inplace_kernel<<<(int)blocks, 256, 0, st>>>(dX, X, n);
+      g_launches++;
+      A2C_LAUNCH_CHECK();
+      if (acc)
+        if (int r3 = channel_sum_launch(dX, nullptr, acc, N, s->Cin, s->H * s->W, st)) return r3;
+    }
+  }
+  if (acc) {
+    f64_to_f32_kernel<<<cdiv(s->Cin, 64), 64, 0, st>>>(acc, dbias_prev, s->Cin);
+    g_launches++;
+    A2C_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int a2c_channel_sum(const float* X, const float* mask, float* out, int N, int C, int HW, void* workspace,
+                    long long workspace_bytes, void* stream) {
+  A2C_ARG_CHECK(X && out && N >= 0 && C > 0 && HW > 0, "channel_sum: bad args");
+  A2C_ARG_CHECK(workspace && workspace_bytes >= (long long)sizeof(double) * C, "channel_sum: workspace of C doubles");
+  cudaStream_t st = as_stream(stream);
+  double* acc = static_cast<double*>(workspace);
+  A2C_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * C, st));
+  if (N > 0)
+    if (int rc = channel_sum_launch(X, mask, acc, N, C, HW, st)) return rc;
+  f64_to_f32_kernel<<<cdiv(C, 64), 64, 0, st>>>(acc, out, C);
+  g_launches++;
+  A2C_LAUNCH_CHECK();
+  return 0;
 }
 
 int a2c_conv2d_fused_mask(const a2c_conv_shape* s, int precision, int input_is_view) {

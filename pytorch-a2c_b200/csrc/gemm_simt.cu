@@ -338,10 +338,20 @@ int gemm_dispatch(GemmParams p, int amode, int bmode, void* workspace, long long
   return 0;
 }
 
+int splitk_reduce(const float* partial, float* C, long long ldc, const float* bias, int M, int N, int splits,
+                  int relu, int beta, cudaStream_t st) {
+  long long blocks = cdivll((long long)M * N, 256);
+  if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+  splitk_reduce_kernel<<<(int)blocks, 256, 0, st>>>(partial, C, ldc, bias, M, N, splits, relu, beta);
+  g_launches++;
+  A2C_LAUNCH_CHECK();
+  return 0;
+}
+
 int gemm_tc_try(const float* A, long long sam, long long sak, const float* B, long long sbk,
                 long long sbn, float* C, long long ldc, const float* bias, int M, int N, int K,
                 int relu, int beta, int precision, void* workspace, long long workspace_bytes,
-                cudaStream_t st);   // gemm_tc.cu; returns 1 when it did not handle the shape
+                const float* cmask, cudaStream_t st);   // gemm_tc.cu; returns 1 when it did not handle the shape
 
 static int check_view(const a2c_state_view* v) {
   A2C_ARG_CHECK(v && v->base, "state view: null");
@@ -363,6 +373,14 @@ int a2c_gemm(const float* A, long long sam, long long sak, const float* B, long 
              long long sbn, float* C, long long ldc, const float* bias, int M, int N, int K,
              int relu, int beta, int precision, void* workspace, long long workspace_bytes,
              void* stream) {
+  return a2c_gemm_masked(A, sam, sak, B, sbk, sbn, C, ldc, bias, nullptr, M, N, K, relu, beta, precision,
+                         workspace, workspace_bytes, stream);
+}
+
+int a2c_gemm_masked(const float* A, long long sam, long long sak, const float* B, long long sbk,
+                    long long sbn, float* C, long long ldc, const float* bias, const float* Cmask, int M,
+                    int N, int K, int relu, int beta, int precision, void* workspace,
+                    long long workspace_bytes, void* stream) {
   A2C_ARG_CHECK(A && B && C, "gemm: null pointer");
   A2C_ARG_CHECK(M >= 0 && N >= 0 && K >= 0 && ldc >= N, "gemm: bad sizes M=%d N=%d K=%d ldc=%lld", M, N, K, ldc);
   A2C_ARG_CHECK(beta == 0 || beta == 1, "gemm: beta must be 0 or 1");
@@ -370,20 +388,30 @@ int a2c_gemm(const float* A, long long sam, long long sak, const float* B, long 
   cudaStream_t st = as_stream(stream);
   if (precision != 0) {
     int rc = gemm_tc_try(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, relu, beta, precision,
-                         workspace, workspace_bytes, st);
+                         workspace, workspace_bytes, Cmask, st);
     if (rc != 1) return rc;   // 0 = done on tensor cores, other = error; 1 = shape not handled
   }
+  A2C_ARG_CHECK(!Cmask || ldc == N, "gemm_masked: the FFMA path needs a contiguous C (ldc == N)");
   GemmParams p{};
   p.A.p = A; p.A.s_mn = sam; p.A.s_k = sak;
   p.B.p = B; p.B.s_mn = sbn; p.B.s_k = sbk;
   p.C = C; p.ldc = ldc; p.bias = bias; p.M = M; p.N = N; p.K = K; p.relu = relu; p.beta = beta;
   const int amode = pick_mode(A, sam, sak, M, K, BK);
   const int bmode = pick_mode(B, sbn, sbk, N, K, BK);
-  return gemm_dispatch(p, amode, bmode, workspace, workspace_bytes, st);
+  if (int rc = gemm_dispatch(p, amode, bmode, workspace, workspace_bytes, st)) return rc;
+  if (Cmask) {
+    const long long n = (long long)M * N;
+    long long blocks = cdivll(n, 256);
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    relu_bwd_kernel<<<(int)blocks, 256, 0, st>>>(C, Cmask, C, n);
+    g_launches++;
+    A2C_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 int a2c_linear_state_fwd(const a2c_state_view* x, const float* W, const float* bias, float* Y, int R,
-                         int Nout, int relu, void* stream) {
+                         int Nout, int relu, void* workspace, long long workspace_bytes, void* stream) {
   if (int rc = check_view(x)) return rc;
   A2C_ARG_CHECK(W && Y && R >= 0 && Nout > 0, "linear_state_fwd: bad args");
   A2C_ARG_CHECK((reinterpret_cast<uintptr_t>(W) & 15) == 0, "linear_state_fwd: W must be 16-byte aligned");
@@ -393,7 +421,8 @@ int a2c_linear_state_fwd(const a2c_state_view* x, const float* W, const float* b
   p.A.view = *x;
   p.B.p = W; p.B.s_mn = K; p.B.s_k = 1;
   p.C = Y; p.ldc = Nout; p.bias = bias; p.M = M; p.N = Nout; p.K = K; p.relu = relu; p.beta = 0;
-  return gemm_dispatch(p, MODE_VIEW_K, MODE_K, nullptr, 0, as_stream(stream));
+  // few output tiles (C1: 60 x 256 = 2 tiles over K = 12,800): split K over the SMs
+  return gemm_dispatch(p, MODE_VIEW_K, MODE_K, workspace, workspace_bytes, as_stream(stream));
 }
 
 int a2c_linear_state_wgrad(const a2c_state_view* x, const float* dY, float* dW, int R, int Nout,

@@ -31,6 +31,8 @@ struct GemmParams {
   int M, N, K;
   int relu, beta;
   int nkb, kb_per_split;
+  float* partial;     // split-K: [splits][M][N] partial products (bias / beta / relu applied by the reduction)
+  const float* cmask; // optional, laid out like C: C = cmask > 0 ? value : 0 (ReLU of the producer of C's forward twin)
 };
 
 constexpr int PROD_THREADS = 256;   // 8 producer warps per operand
@@ -124,13 +126,31 @@ struct GemmProblem {
     gemm_store<BN, SPLIT3>(p.B, f, hi, lo, t);
   }
   template <int HALF>
-  static __device__ __forceinline__ void epilogue(const Params& p, int row, int nb, const float* acc, int) {
+  static __device__ __forceinline__ void epilogue(const Params& p, int row, int nb, const float* acc, int split) {
     if (row >= p.M) return;
+    if (p.partial) {
+      float* dst = p.partial + ((long long)split * p.M + row) * p.N + nb;
+#pragma unroll
+      for (int j = 0; j < HALF; ++j)
+        if (nb + j < p.N) dst[j] = acc[j];
+      return;
+    }
     float* dst = p.C + (long long)row * p.ldc + nb;
     const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (nb + HALF <= p.N);
+    const float* msk = p.cmask ? p.cmask + (long long)row * p.ldc + nb : nullptr;
+    const bool mvec = msk && vec && ((reinterpret_cast<uintptr_t>(msk) & 15) == 0);
 #pragma unroll
     for (int j = 0; j < HALF; j += 4) {
       float x[4];
+      float mk[4] = {1.f, 1.f, 1.f, 1.f};
+      if (mvec) {
+        const float4 m4 = __ldg(reinterpret_cast<const float4*>(msk + j));
+        mk[0] = m4.x; mk[1] = m4.y; mk[2] = m4.z; mk[3] = m4.w;
+      } else if (msk) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (nb + j + q < p.N) mk[q] = __ldg(msk + j + q);
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int n = nb + j + q;
@@ -139,6 +159,7 @@ struct GemmProblem {
           if (p.bias) val += p.bias[n];
           if (p.beta) val += dst[j + q];
           if (p.relu) val = fmaxf(val, 0.0f);
+          if (!(mk[q] > 0.0f)) val = 0.0f;
         }
         x[q] = val;
       }
@@ -162,8 +183,8 @@ static bool classify(const float* ptr, long long s_mn, long long s_k, int MN, in
 }
 
 template <int BN, bool SPLIT3>
-static int launch_gemm(const GemmParams& p, cudaStream_t st) {
-  int rc = tc_launch<BN, SPLIT3, GemmProblem<BN, SPLIT3>>(p, cdiv(p.M, TM), cdiv(p.N, BN), 1, st);
+static int launch_gemm(const GemmParams& p, int splits, cudaStream_t st) {
+  int rc = tc_launch<BN, SPLIT3, GemmProblem<BN, SPLIT3>>(p, cdiv(p.M, TM), cdiv(p.N, BN), splits, st);
   if (rc) return rc;
   g_launches++;
   A2C_LAUNCH_CHECK();
@@ -174,35 +195,59 @@ static int launch_gemm(const GemmParams& p, cudaStream_t st) {
 
 // Returns 0 when the GEMM ran on the tensor cores, 1 when the shape does not
 // qualify (caller falls back to the fp32 FFMA kernel), anything else = error.
+int splitk_reduce(const float* partial, float* C, long long ldc, const float* bias, int M, int N, int splits,
+                  int relu, int beta, cudaStream_t st);   // gemm_simt.cu
+
 int gemm_tc_try(const float* A, long long sam, long long sak, const float* B, long long sbk,
                 long long sbn, float* C, long long ldc, const float* bias, int M, int N, int K,
                 int relu, int beta, int precision, void* workspace, long long workspace_bytes,
-                cudaStream_t st) {
-  (void)workspace; (void)workspace_bytes;
+                const float* cmask, cudaStream_t st) {
   // tiny problems are launch-latency bound and gain nothing from a 128-row MMA tile
   if (M < 64 || K < 64 || (long long)M * N * K < (1ll << 22)) return 1;
   tc::GemmParams p{};
   if (!tc::classify(A, sam, sak, M, K, &p.A)) return 1;
   if (!tc::classify(B, sbn, sbk, N, K, &p.B)) return 1;
   p.C = C; p.ldc = ldc; p.bias = bias; p.M = M; p.N = N; p.K = K; p.relu = relu; p.beta = beta;
+  p.cmask = cmask;
   p.nkb = cdiv(K, tc::KB); p.kb_per_split = p.nkb;
   const bool split3 = (precision == 1);
   int bn = N > 64 ? 128 : (N > 32 ? 64 : 32);
   // prefer more CTAs when the grid would not fill the machine
   const int sms = num_sms();
   while (bn > 64 && (long long)cdiv(N, bn) * cdiv(M, tc::TM) < sms) bn >>= 1;
+  // Split-K: an output with few tiles and a long reduction (weight gradients: dW[256, 256] over
+  // K = 16,384 samples is 4 tiles) would keep a handful of SMs busy; split K over the others and
+  // reduce the partial products (fp32, fixed order) in a second small kernel.
+  int splits = 1;
+  const long long tiles = (long long)cdiv(N, bn) * cdiv(M, tc::TM);
+  if (workspace && !cmask && tiles * 2 <= sms && p.nkb >= 64) {        // K >= 2048
+    long long want = sms / tiles;
+    if (want > p.nkb / 8) want = p.nkb / 8;                 // at least 8 k-blocks (256 k) per split
+    const long long per = (long long)M * N * (long long)sizeof(float);
+    if (want * per > workspace_bytes) want = workspace_bytes / per;
+    if (want > 1) splits = (int)want;
+  }
+  if (splits > 1) {
+    p.kb_per_split = cdiv(p.nkb, splits);
+    splits = cdiv(p.nkb, p.kb_per_split);
+    p.partial = static_cast<float*>(workspace);
+  }
+  int rc;
   if (split3) {
     switch (bn) {
-      case 128: return tc::launch_gemm<128, true>(p, st);
-      case 64: return tc::launch_gemm<64, true>(p, st);
-      default: return tc::launch_gemm<32, true>(p, st);
+      case 128: rc = tc::launch_gemm<128, true>(p, splits, st); break;
+      case 64: rc = tc::launch_gemm<64, true>(p, splits, st); break;
+      default: rc = tc::launch_gemm<32, true>(p, splits, st); break;
+    }
+  } else {
+    switch (bn) {
+      case 128: rc = tc::launch_gemm<128, false>(p, splits, st); break;
+      case 64: rc = tc::launch_gemm<64, false>(p, splits, st); break;
+      default: rc = tc::launch_gemm<32, false>(p, splits, st); break;
     }
   }
-  switch (bn) {
-    case 128: return tc::launch_gemm<128, false>(p, st);
-    case 64: return tc::launch_gemm<64, false>(p, st);
-    default: return tc::launch_gemm<32, false>(p, st);
-  }
+  if (rc || splits == 1) return rc;
+  return splitk_reduce(p.partial, C, ldc, bias, M, N, splits, relu, beta, st);
 }
 
 }  // namespace a2c

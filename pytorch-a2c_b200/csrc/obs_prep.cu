@@ -9,15 +9,20 @@
 // 44,800 algorithmic bytes per transition, HBM-bound.
 //
 // Variant 0 (default): persistent CTAs, one 3-D TMA box (120 u32 x 80 rows x 1
-// frame; row pitch 960 B skips the odd rows) per frame into a 4-deep shared
-// memory ring guarded by mbarriers; threads then pick byte 6k of every row with
-// conflict-free 128-bit shared loads and classify 4 pixels per SIMD compare.
+// frame; row pitch 960 B skips the odd rows) per frame into a shared memory ring
+// guarded by mbarriers (two CTAs per SM with a 2-deep ring each: one CTA's loads
+// and classification fill the other's barrier / refill bubbles); threads then
+// pick byte 6k of every row with 128-bit shared loads and classify 4 pixels per
+// SIMD compare.  Variant 2: one CTA per SM with a 4-deep ring (the round-1 shape).
 // Variant 1: same arithmetic straight from global memory with 128-bit loads.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -32,6 +37,20 @@ void set_error(const char* fmt, ...) {
 }
 std::atomic<long long> g_launches{0};
 
+cudaError_t set_max_dynamic_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;      // (kernel, device) -> bytes granted
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = done.find({kernel, dev});
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[{kernel, dev}] = bytes;
+  return e;
+}
+
 constexpr int FRAME_H = 210, FRAME_W = 160, FRAME_C = 3;
 constexpr int ROW_BYTES = FRAME_W * FRAME_C;         // 480
 constexpr int FRAME_BYTES = FRAME_H * ROW_BYTES;     // 100800
@@ -39,8 +58,9 @@ constexpr int CROP_TOP = 35;
 constexpr int OUT = 80;                              // 80 x 80 plane
 constexpr int PLANE_BYTES = OUT * OUT;               // 6400
 constexpr int SEL_BYTES = OUT * ROW_BYTES;           // 38400 selected-row bytes per frame
+constexpr int BAND_ROWS = 2 * OUT - 1;               // source rows 35 .. 193
+constexpr int BAND_BYTES = BAND_ROWS * ROW_BYTES;    // 76320
 constexpr int ITEMS = OUT * 10;                      // 800 work items of 48 B -> 8 px
-constexpr int STAGES = 4;
 constexpr int PREP_THREADS = 256;
 
 // 48 input bytes (12 words, w[2], w[5], w[8], w[11] unused) -> 8 output bytes.
@@ -54,7 +74,10 @@ __device__ __forceinline__ uint2 classify48(const uint4 a, const uint4 b, const 
   return make_uint2(~bg_lo & 0x01010101u, ~bg_hi & 0x01010101u);
 }
 
-__global__ void __launch_bounds__(PREP_THREADS, 1)
+// STAGES x CTAS: 4-deep ring with one CTA per SM, or 2-deep rings with two CTAs per SM (the
+// second CTA's loads and classification fill the first one's barrier / refill bubbles).
+template <int STAGES, int CTAS>
+__global__ void __launch_bounds__(PREP_THREADS, CTAS)
 obs_prep_tma_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t* __restrict__ reset,
                     uint8_t* __restrict__ planes, uint8_t* __restrict__ pflag, int NF, int F,
                     int P, int j0) {
@@ -202,8 +225,24 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 void* tensormap_encoder() { return reinterpret_cast<void*>(get_encode()); }
 
+template <int STAGES, int CTAS>
+static int launch_prep_tma(const CUtensorMap& tmap, const uint8_t* reset, uint8_t* planes, uint8_t* pflag,
+                           int NF, int F, int P, int j0, cudaStream_t st) {
+  const int smem = STAGES * SEL_BYTES + STAGES * 8;
+  auto kern = obs_prep_tma_kernel<STAGES, CTAS>;
+  A2C_CUDA_CHECK(set_max_dynamic_smem(reinterpret_cast<const void*>(kern), smem));
+  const int cap = num_sms() * CTAS;
+  const int grid = NF < cap ? NF : cap;
+  kern<<<grid, PREP_THREADS, smem, st>>>(tmap, reset, planes, pflag, NF, F, P, j0);
+  return 0;
+}
+
+// Source layouts: packed == 0: raw frames u8 [NF, 210, 160, 3] (the TMA row pitch of 960 B skips
+// the even rows); packed == 1: the 80 selected rows only, u8 [NF, 80, 480]; packed == 2: the
+// cropped band, source rows 35..193, u8 [NF, 159, 480] (the staging layouts of
+// a2c_obs_ingest_rows_async).
 static int launch_prep(const uint8_t* frames, const uint8_t* reset, uint8_t* planes, uint8_t* pflag,
-                       int R, int F, int P, int j0, int variant, cudaStream_t st) {
+                       int R, int F, int P, int j0, int variant, int packed, cudaStream_t st) {
   A2C_ARG_CHECK(frames && reset && planes && pflag, "obs_prep: null pointer");
   A2C_ARG_CHECK(R >= 0 && F >= 0 && P > 0 && j0 >= 0 && j0 + F <= P,
                 "obs_prep: bad sizes R=%d F=%d P=%d j0=%d", R, F, P, j0);
@@ -214,7 +253,7 @@ static int launch_prep(const uint8_t* frames, const uint8_t* reset, uint8_t* pla
   A2C_ARG_CHECK(nf_ll < (1ll << 31), "obs_prep: too many frames");
   const int NF = (int)nf_ll;
   if (NF == 0) return 0;
-  if (variant == 0) {
+  if (variant == 0 || variant == 2) {
     auto encode = get_encode();
     if (!encode) {
       set_error("obs_prep: cuTensorMapEncodeTiled unavailable");
@@ -223,26 +262,25 @@ static int launch_prep(const uint8_t* frames, const uint8_t* reset, uint8_t* pla
     CUtensorMap tmap;
     cuuint64_t dims[3] = {ROW_BYTES / 4, OUT, (cuuint64_t)NF};
     cuuint64_t strides[2] = {2 * ROW_BYTES, FRAME_BYTES};   // bytes, dims 1..2
+    if (packed == 1) { strides[0] = ROW_BYTES; strides[1] = SEL_BYTES; }
+    if (packed == 2) strides[1] = BAND_BYTES;
     cuuint32_t box[3] = {ROW_BYTES / 4, OUT, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3,
-                         const_cast<uint8_t*>(frames) + CROP_TOP * ROW_BYTES, dims, strides, box, estr,
+                         const_cast<uint8_t*>(frames) + (packed ? 0 : CROP_TOP * ROW_BYTES), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) {
       set_error("obs_prep: cuTensorMapEncodeTiled failed (%d)", (int)cr);
       return (int)cudaErrorInvalidValue;
     }
-    const int smem = STAGES * SEL_BYTES + STAGES * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-      A2C_CUDA_CHECK(cudaFuncSetAttribute(obs_prep_tma_kernel,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_set = true;
-    }
-    const int grid = NF < num_sms() ? NF : num_sms();
-    obs_prep_tma_kernel<<<grid, PREP_THREADS, smem, st>>>(tmap, reset, planes, pflag, NF, F, P, j0);
+    // measured on B200 (5,120 frames): 2 CTAs/SM x 2 stages 39.6 us (5.79 TB/s of algorithmic bytes),
+    // 1 CTA/SM x 4 stages 44.1 us (5.20 TB/s)
+    int rc = variant == 2 ? launch_prep_tma<4, 1>(tmap, reset, planes, pflag, NF, F, P, j0, st)
+                          : launch_prep_tma<2, 2>(tmap, reset, planes, pflag, NF, F, P, j0, st);
+    if (rc) return rc;
   } else {
+    A2C_ARG_CHECK(!packed, "obs_prep: the direct-load variant reads raw frames only");
     long long blocks = cdivll((long long)NF * ITEMS, 256);
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
@@ -265,7 +303,46 @@ long long a2c_launch_count(void) { return a2c::g_launches.load(); }
 
 int a2c_obs_prep_stack(const uint8_t* frames, const uint8_t* reset, uint8_t* planes, uint8_t* pflag,
                        int R, int F, int P, int j0, int variant, void* stream) {
-  return launch_prep(frames, reset, planes, pflag, R, F, P, j0, variant, as_stream(stream));
+  return launch_prep(frames, reset, planes, pflag, R, F, P, j0, variant, 0, as_stream(stream));
+}
+
+int a2c_obs_prep_stack_rows(const uint8_t* rows, const uint8_t* reset, uint8_t* planes, uint8_t* pflag,
+                            int R, int F, int P, int j0, int layout, void* stream) {
+  A2C_ARG_CHECK(layout >= 0 && layout <= 2, "obs_prep_rows: layout must be 0, 1 or 2");
+  return launch_prep(rows, reset, planes, pflag, R, F, P, j0, 0, layout == 0 ? 1 : (layout == 1 ? 2 : 0),
+                     as_stream(stream));
+}
+
+long long a2c_obs_ingest_bytes_per_frame(int layout) {
+  return layout == 0 ? SEL_BYTES : (layout == 1 ? BAND_BYTES : FRAME_BYTES);
+}
+
+int a2c_obs_ingest_rows_async(const uint8_t* frames_host, uint8_t* rows, long long n_frames, int layout,
+                              void* stream) {
+  A2C_ARG_CHECK(frames_host && rows && n_frames >= 0 && layout >= 0 && layout <= 2, "obs_ingest: bad args");
+  if (n_frames == 0) return 0;
+  if (layout == 2) {                       // whole frames, one contiguous copy
+    A2C_CUDA_CHECK(cudaMemcpyAsync(rows, frames_host, (size_t)n_frames * FRAME_BYTES, cudaMemcpyHostToDevice,
+                                   as_stream(stream)));
+    return 0;
+  }
+  if (layout == 1) {                       // the cropped band of every frame: 76,320 contiguous bytes each
+    A2C_CUDA_CHECK(cudaMemcpy2DAsync(rows, BAND_BYTES, frames_host + CROP_TOP * ROW_BYTES, FRAME_BYTES, BAND_BYTES,
+                                     (size_t)n_frames, cudaMemcpyHostToDevice, as_stream(stream)));
+    return 0;
+  }
+  // layout 0: source seen as [n_frames][105 double rows][960 B], of which double rows 17..96,
+  // bytes 480..959 (= source rows 35, 37, ..., 193) are copied: 38,400 B per frame.
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof(p));
+  p.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(frames_host), 2 * ROW_BYTES, 2 * ROW_BYTES, FRAME_H / 2);
+  p.srcPos = make_cudaPos(ROW_BYTES, CROP_TOP / 2, 0);
+  p.dstPtr = make_cudaPitchedPtr(rows, ROW_BYTES, ROW_BYTES, OUT);
+  p.dstPos = make_cudaPos(0, 0, 0);
+  p.extent = make_cudaExtent(ROW_BYTES, OUT, (size_t)n_frames);
+  p.kind = cudaMemcpyHostToDevice;
+  A2C_CUDA_CHECK(cudaMemcpy3DAsync(&p, as_stream(stream)));
+  return 0;
 }
 
 int a2c_obs_prep_stack_host(const uint8_t* frames_host, const uint8_t* reset_host, uint8_t* planes,
@@ -282,7 +359,7 @@ int a2c_obs_prep_stack_host(const uint8_t* frames_host, const uint8_t* reset_hos
   A2C_ARG_CHECK(at2.type == cudaMemoryTypeHost && at2.devicePointer != nullptr,
                 "obs_prep_host: reset must be pinned (page-locked, mapped) host memory");
   int rc = launch_prep(static_cast<const uint8_t*>(at.devicePointer),
-                       static_cast<const uint8_t*>(at2.devicePointer), planes, pflag, R, F, P, j0, 0,
+                       static_cast<const uint8_t*>(at2.devicePointer), planes, pflag, R, F, P, j0, 0, 0,
                        as_stream(stream));
   if (rc) return rc;
   A2C_CUDA_CHECK(cudaStreamSynchronize(as_stream(stream)));

@@ -16,9 +16,21 @@ extern std::atomic<long long> g_launches;
 
 // ---------------------------------------------------------------------------
 // a2c/runner.py:228-245 + a2c/utils.py:63-79, one thread per rollout slot.
+//
+// Why one thread per slot and not a warp-shuffle scan: the reference evaluates
+//   rs = a[i] + g * rs   sequentially in fp32 (utils.py:76-77) and parity for the
+// scans is BIT-exact.  A parallel (shuffle) scan composes the affine maps
+// (a, g) o (a', g') = (a + g a', g g'), which rounds differently from the
+// sequential recurrence, so the recurrence stays sequential inside a slot and
+// the parallelism is across the R slots (a warp = 32 slots).  What a warp
+// should not do is read global memory with a stride of T floats: the staged
+// kernel below moves whole [slots x T] tiles through shared memory with
+// coalesced accesses (odd row pitch -> conflict-free column walks) and each
+// thread walks its slot there.  The direct kernel is the fallback for T too
+// large for a shared-memory tile.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-delta_scan_kernel(float* __restrict__ rewards, float* __restrict__ dones,
+delta_scan_direct_kernel(float* __restrict__ rewards, float* __restrict__ dones,
                   const float* __restrict__ values, float* __restrict__ deltas,
                   float* __restrict__ advs, float* __restrict__ returns, double* __restrict__ stats,
                   int R, int T, float gamma, float gl) {
@@ -74,6 +86,88 @@ delta_scan_kernel(float* __restrict__ rewards, float* __restrict__ dones,
   }
 }
 
+// Staged variant: a block owns SB consecutive slots.  Tiles: rew, done (in place), val -> adv
+// (in place: v[t] is consumed before adv[t] is written), delta, ret.
+__global__ void __launch_bounds__(64)
+delta_scan_staged_kernel(float* __restrict__ rewards, float* __restrict__ dones,
+                         const float* __restrict__ values, float* __restrict__ deltas,
+                         float* __restrict__ advs, float* __restrict__ returns, double* __restrict__ stats,
+                         int R, int T, int SB, int TP, float gamma, float gl) {
+  extern __shared__ float tile[];
+  __shared__ double scratch[32];
+  float* s_rew = tile;                       // [SB][TP]
+  float* s_done = s_rew + SB * TP;
+  float* s_val = s_done + SB * TP;           // [SB][TP], T + 1 <= TP; becomes adv
+  float* s_delta = s_val + SB * TP;
+  float* s_ret = s_delta + SB * TP;
+  const int r0 = blockIdx.x * SB;
+  const int nslot = min(SB, R - r0);
+  const long long g0 = (long long)r0 * T;
+  const int nel = nslot * T;
+  for (int i = threadIdx.x; i < nel; i += blockDim.x) {
+    const int sl = i / T, t = i - sl * T;
+    s_rew[sl * TP + t] = rewards[g0 + i];
+    s_done[sl * TP + t] = dones[g0 + i];
+  }
+  const long long v0 = (long long)r0 * (T + 1);
+  for (int i = threadIdx.x; i < nslot * (T + 1); i += blockDim.x) {
+    const int sl = i / (T + 1), t = i - sl * (T + 1);
+    s_val[sl * TP + t] = values[v0 + i];
+  }
+  __syncthreads();
+  double s_a = 0, s_a2 = 0, s_r = 0, s_r2 = 0;
+  for (int sl = threadIdx.x; sl < nslot; sl += blockDim.x) {
+    float* rw = s_rew + sl * TP;
+    float* dn = s_done + sl * TP;
+    float* v = s_val + sl * TP;
+    float rew = rw[T - 1], d = dn[T - 1];
+    if (d == 0.0f) {                                   // runner.py:236-243
+      rew = __fadd_rn(rew, __fmul_rn(gamma, v[T]));
+      d = 1.0f;
+      rw[T - 1] = rew;
+      dn[T - 1] = d;
+    }
+    float adv_rs = 0.0f, ret_rs = 0.0f, v_next = 0.0f;
+    for (int t = T - 1; t >= 0; --t) {
+      if (t != T - 1) { rew = rw[t]; d = dn[t]; }
+      const float vt = v[t];
+      float delta;
+      if (t == T - 1)
+        delta = __fsub_rn(rew, vt);                    // runner.py:244
+      else                                             // runner.py:231
+        delta = __fsub_rn(__fadd_rn(rew, __fmul_rn(__fmul_rn(gamma, v_next), __fsub_rn(1.0f, d))), vt);
+      if (d == 1.0f) { adv_rs = 0.0f; ret_rs = 0.0f; }       // utils.py:76
+      adv_rs = __fadd_rn(delta, __fmul_rn(gl, adv_rs));      // utils.py:77
+      ret_rs = __fadd_rn(rew, __fmul_rn(gamma, ret_rs));
+      s_delta[sl * TP + t] = delta;
+      v[t] = adv_rs;
+      s_ret[sl * TP + t] = ret_rs;
+      s_a += adv_rs; s_a2 += (double)adv_rs * adv_rs;
+      s_r += ret_rs; s_r2 += (double)ret_rs * ret_rs;
+      v_next = vt;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nel; i += blockDim.x) {
+    const int sl = i / T, t = i - sl * T, o = sl * TP + t;
+    rewards[g0 + i] = s_rew[o];
+    dones[g0 + i] = s_done[o];
+    deltas[g0 + i] = s_delta[o];
+    if (advs) advs[g0 + i] = s_val[o];
+    if (returns) returns[g0 + i] = s_ret[o];
+  }
+  if (stats) {
+    s_a = block_sum(s_a, scratch);
+    s_a2 = block_sum(s_a2, scratch);
+    s_r = block_sum(s_r, scratch);
+    s_r2 = block_sum(s_r2, scratch);
+    if (threadIdx.x == 0) {
+      atomicAdd(&stats[0], s_a); atomicAdd(&stats[1], s_a2);
+      atomicAdd(&stats[2], s_r); atomicAdd(&stats[3], s_r2);
+    }
+  }
+}
+
 // utils.discount on a flat buffer: the thread sitting on a segment end walks
 // its segment backwards, so every segment is summed sequentially (bit-exact).
 __global__ void __launch_bounds__(256)
@@ -96,6 +190,43 @@ discount_kernel(const float* __restrict__ a, const float* __restrict__ dones,
     s1 = block_sum(s1, scratch);
     s2 = block_sum(s2, scratch);
     if (threadIdx.x == 0) { atomicAdd(&stats[0], s1); atomicAdd(&stats[1], s2); }
+  }
+}
+
+// Both scans of an update (a2c/updater.py:70-71 and :86-88) in one launch: advs from deltas with
+// factor ga, returns from rewards with factor gb (b may be NULL: use_nstep_rets).  Same
+// segment-end walk as above, so both are bit-exact.  stats f64 [4]: sum / sumsq of each.
+__global__ void __launch_bounds__(256)
+discount2_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ dones,
+                 float* __restrict__ outa, float* __restrict__ outb, double* __restrict__ stats, long long N,
+                 float ga, float gb) {
+  __shared__ double scratch[32];
+  double a1 = 0, a2 = 0, b1 = 0, b2 = 0;
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < N && (i == N - 1 || dones[i] == 1.0f)) {
+    float ra = 0.0f, rb = 0.0f;
+    long long j = i;
+    do {
+      ra = __fadd_rn(a[j], __fmul_rn(ga, ra));
+      outa[j] = ra;
+      a1 += ra; a2 += (double)ra * ra;
+      if (b) {
+        rb = __fadd_rn(b[j], __fmul_rn(gb, rb));
+        outb[j] = rb;
+        b1 += rb; b2 += (double)rb * rb;
+      }
+      --j;
+    } while (j >= 0 && dones[j] != 1.0f);
+  }
+  if (stats) {
+    a1 = block_sum(a1, scratch);
+    a2 = block_sum(a2, scratch);
+    b1 = block_sum(b1, scratch);
+    b2 = block_sum(b2, scratch);
+    if (threadIdx.x == 0) {
+      atomicAdd(&stats[0], a1); atomicAdd(&stats[1], a2);
+      if (b) { atomicAdd(&stats[2], b1); atomicAdd(&stats[3], b2); }
+    }
   }
 }
 
@@ -214,9 +345,33 @@ int a2c_delta_scan(float* rewards, float* dones, const float* values, float* del
   A2C_ARG_CHECK(rewards && dones && values && deltas, "delta_scan: null pointer");
   A2C_ARG_CHECK(R >= 0 && T >= 1, "delta_scan: bad sizes R=%d T=%d", R, T);
   if (R == 0) return 0;
-  delta_scan_kernel<<<cdiv(R, 128), 128, 0, as_stream(stream)>>>(rewards, dones, values, deltas, advs,
-                                                               returns, stats, R, T, gamma,
-                                                               gamma_lambda);
+  // staged through shared memory when a [slots x T] tile set fits in 48 KB
+  const int TP = (T + 1) | 1;                       // odd pitch >= T + 1
+  int SB = 0;
+  for (int c = 64; c >= 8; c >>= 1)
+    if ((size_t)5 * c * TP * sizeof(float) <= 48 * 1024) { SB = c; break; }
+  if (SB) {
+    const size_t smem = (size_t)5 * SB * TP * sizeof(float);
+    delta_scan_staged_kernel<<<cdiv(R, SB), 64, smem, as_stream(stream)>>>(
+        rewards, dones, values, deltas, advs, returns, stats, R, T, SB, TP, gamma, gamma_lambda);
+  } else {
+    delta_scan_direct_kernel<<<cdiv(R, 128), 128, 0, as_stream(stream)>>>(rewards, dones, values, deltas, advs,
+                                                                        returns, stats, R, T, gamma,
+                                                                        gamma_lambda);
+  }
+  g_launches++;
+  A2C_LAUNCH_CHECK();
+  return 0;
+}
+
+int a2c_discount2(const float* deltas, const float* rewards, const float* dones, float* advs,
+                  float* returns, double* stats, long long N, float gamma_lambda, float gamma,
+                  void* stream) {
+  A2C_ARG_CHECK(deltas && dones && advs && N >= 0, "discount2: bad args");
+  A2C_ARG_CHECK(!rewards || returns, "discount2: returns required when rewards are given");
+  if (N == 0) return 0;
+  discount2_kernel<<<(int)cdivll(N, 256), 256, 0, as_stream(stream)>>>(deltas, rewards, dones, advs, returns,
+                                                                    stats, N, gamma_lambda, gamma);
   g_launches++;
   A2C_LAUNCH_CHECK();
   return 0;

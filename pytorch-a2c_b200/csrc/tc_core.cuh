@@ -396,14 +396,12 @@ int tc_launch(const typename P::Params& p, int mtiles, int ntiles, int splits, c
   if (stages < 2) return 1;
   const size_t smem = (size_t)stages * SB + 1024 /*align slack*/ + SCRATCH_BYTES + (2 * stages + 4) * 8 + 16;
   auto kern = tc_kernel<BN, SPLIT3, P>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  {
+    cudaError_t e = set_max_dynamic_smem(reinterpret_cast<const void*>(kern), (int)(227 * 1024));
     if (e != cudaSuccess) {
       set_error("tc_launch: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return (int)e;
     }
-    configured = true;
   }
   // one CTA per SM (the tile ring takes most of shared memory): persistent over the output tiles
   int ncta = num_sms() / (splits > 0 ? splits : 1);
