@@ -32,6 +32,12 @@ import sys
 import threading
 import time
 
+# NOTE: torch's default (non-expandable) allocator segments are used on purpose.  Measured on B200
+# (GRU config, 400 launches per step): PYTORCH_CUDA_ALLOC_CONF=expandable_segments:True makes step
+# times erratic (57 ... 137 ms, GPU idle while segments are re-mapped) where the default allocator
+# gives 57.0 - 57.4 ms; the first steps of a fresh process are kept out of the timed region by
+# Workload.settle() instead.
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "pytorch-a2c_b200")):
     if p not in sys.path:
@@ -176,7 +182,7 @@ def pinned_copy(t):
 class Workload:
     """Resident state of one benchmark configuration on this rank."""
 
-    def __init__(self, name, world, rank, dev, precision, dist):
+    def __init__(self, name, world, rank, dev, precision, dist, data_parallel=True):
         from a2c_b200 import models, ops, updater
         self.ops, self.dist = ops, dist
         self.name, self.world, self.rank, self.dev = name, world, rank, dev
@@ -188,7 +194,7 @@ class Workload:
         ops.set_precision(precision)
         torch.manual_seed(0)
         self.net = models.get_model_class(model)([fs, 80, 80], 3, h_size=HYPS["h_size"]).to(dev)
-        self.upd = updater.Updater(self.net, self.hyps)
+        self.upd = updater.Updater(self.net, self.hyps, data_parallel=data_parallel)
         if world > 1:                       # identical replicas: broadcast rank 0's init
             dist.broadcast(self.upd.flat.flat, 0)
         b = synth_batch(R, T, dev, 1234 + rank)
@@ -257,16 +263,21 @@ class Workload:
         if profile:
             _lib.PROFILE = {}
         launches0 = _lib.launch_count()
+        mallocs0 = torch.cuda.memory_stats(self.dev).get("num_device_alloc", 0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         e0.record()
         info = None
         if from_host:
             self.ingest.prefetch(self.h_frames, self.h_reset)       # step 0's copy: inside the timed region
         for i in range(steps):
             info = self.step(from_host, prefetch_next=(i + 1 < steps))
+            marks[i].record()
         e1.record()
         self.barrier()
         ms = e0.elapsed_time(e1)
+        self.last_step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
+        self.last_device_allocs = torch.cuda.memory_stats(self.dev).get("num_device_alloc", 0) - mallocs0
         prof = _lib.PROFILE
         _lib.PROFILE = None
         if self.world > 1:
@@ -274,6 +285,28 @@ class Workload:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, _lib.launch_count() - launches0, info, prof
+
+    def settle(self, max_steps=30, window=3, tol=1.03):
+        """Untimed steps BEFORE the W warm-up steps until `window` consecutive step times agree
+        within 3 % (at most `max_steps`).  A fresh process on a box whose previous tenant has just
+        released tens of GB showed 2x slower, erratic steps for its first second or two; this
+        keeps that transient out of the warm-up / timed region.  The count is reported."""
+        times = []
+        for i in range(max_steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            self.step(False)
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+            done = len(times) >= window and max(times[-window:]) <= tol * min(times[-window:])
+            if self.world > 1:                  # every rank leaves the loop after the same step
+                flag = torch.tensor([1 if done else 0], device=self.dev)
+                self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+                done = bool(flag.item())
+            if done:
+                break
+        return len(times)
 
     def host_enqueue_ms(self, reps=3):
         """Host time to ENQUEUE one step (everything up to, not including, the read-back of the
@@ -342,26 +375,31 @@ class Workload:
 
 def measure(wl, steps, warmup, pk, precision, profile_steps=3, with_stage1=True):
     """value / e2e / kernel table / rooflines of one workload (all ranks call this)."""
+    settle = wl.settle()
     for _ in range(warmup):
         wl.step(False)
     ms, launches, info, _ = wl.timed(False, steps)
+    step_ms, dev_allocs = wl.last_step_ms, wl.last_device_allocs
     for _ in range(max(1, min(2, warmup))):
         wl.ingest.prefetch(wl.h_frames, wl.h_reset)
         wl.step(True)
     ms_e2e, _, _, _ = wl.timed(True, steps)
+    e2e_step_ms = wl.last_step_ms
     _, _, _, prof = wl.timed(False, min(steps, profile_steps), profile=True)
     stage1_ms = wl.stage1_alone_ms() if with_stage1 else None
     host_ms = wl.host_enqueue_ms()
     total_tr = wl.N * wl.world * steps
     rec = {"ms_per_step": ms / steps, "value": total_tr / (ms / 1e3),
            "e2e": {"value": total_tr / (ms_e2e / 1e3), "unit": "transitions/s",
-                   "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": wl.h2d_bytes(),
+                   "ms_per_step": ms_e2e / steps, "step_ms": e2e_step_ms, "h2d_bytes_per_step": wl.h2d_bytes(),
                    "d2h_bytes_per_step": 20,
-                   "h2d_note": "per step ONE strided DMA moves the 80 selected rows (38,400 of 100,800 B) "
-                               "of each new frame from pinned host memory to a device staging buffer, "
+                   "h2d_note": "per step ONE asynchronous DMA (staging layout %d: %d of 100,800 B per frame cross "
+                               "PCIe) moves the new frames from pinned host memory to a device staging buffer, "
                                "pipelined under the previous step's kernels; stage 1 then reads the staging "
-                               "buffer.  Rollout scalars are copied on the compute stream."},
+                               "buffer.  Rollout scalars are copied on the compute stream, before the DMA is "
+                               "queued." % (wl.ingest.layout, wl.ingest.frame_bytes)},
            "gpu_launches": int(launches), "loss": info["Loss"], "host_enqueue_ms_per_step": host_ms,
+           "step_ms": step_ms, "device_allocs_in_timed_region": dev_allocs, "settle_steps": settle,
            "update_micro_batches": wl.upd.last_chunks}
     roof, table, stages = roofline_from_profile(prof, min(steps, profile_steps), wl.R, wl.T, pk, stage1_ms,
                                                 precision)
@@ -469,8 +507,12 @@ def dp_parity(world, rank, dev, dist, precision):
         den = float(g1.abs().max())
         out = {"max_rel_grad_diff": float((g_dp - g1).abs().max()) / den,
                "rel_l2_grad_diff": float((g_dp - g1).double().norm() / g1.double().norm()),
-               "max_rel_loss_diff": float(((loss_dp - res1["loss_terms"]).abs()
-                                           / res1["loss_terms"].abs().clamp_min(1e-12)).max()),
+               # loss terms (Loss, Pi_Loss, ValLoss, Entropy) on the scale the parity tests use:
+               # |diff| / max(1, |value|)  (Pi_Loss is a near-zero sum of signed terms)
+               "max_loss_diff": float(((loss_dp - res1["loss_terms"]).abs()
+                                       / res1["loss_terms"].abs().clamp_min(1.0)).max()),
+               "loss_terms_dp": [float(x) for x in loss_dp.tolist()],
+               "loss_terms_full_batch": [float(x) for x in res1["loss_terms"].tolist()],
                "config": "ConvModel, %d slots x %d steps global, %d slots per rank, micro-batches of 2 slots, "
                          "vs one full-batch pass on rank 0" % (Rg, T, Rg // world)}
     dist.barrier()
@@ -564,6 +606,9 @@ def run_ours(args):
             "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"],
             "roofline": rec["roofline"], "kernel_table": rec["kernel_table"], "stages": rec["stages"],
             "clocks": clocks, "loss": rec["loss"], "peaks_source": pk["src"],
+            "step_ms": rec["step_ms"], "host_enqueue_ms_per_step": rec["host_enqueue_ms_per_step"],
+            "device_allocs_in_timed_region": rec["device_allocs_in_timed_region"],
+            "settle_steps": rec["settle_steps"],
         }
         if allred is not None:
             out["allreduce"] = allred
@@ -571,6 +616,25 @@ def run_ours(args):
             out["dp_parity"] = parity
     del wl
     torch.cuda.empty_cache()
+
+    if world > 1 and workload == "c5" and not args.no_extras:
+        # the denominator of the strong-scaling curve, measured in the same run: all 4096 envs on
+        # rank 0 alone (no collectives), the other ranks wait
+        n1 = None
+        if rank == 0:
+            w1 = Workload("c5", 1, 0, dev, args.precision, dist, data_parallel=False)
+            for _ in range(3):
+                w1.step(False)
+            ms1, _, _, _ = w1.timed(False, 3)
+            n1 = {"value": w1.N * 3 / (ms1 / 1e3), "ms_per_step": ms1 / 3, "steps": 3, "warmup": 3,
+                  "update_micro_batches": w1.upd.last_chunks,
+                  "what": "C5 (4096 envs x 20 steps) on ONE GPU of this box, same build, measured by rank 0 "
+                          "while the other ranks idle: value / (n_gpus x this) is the strong-scaling efficiency"}
+            del w1
+            torch.cuda.empty_cache()
+        dist.barrier()
+        if rank == 0:
+            out["c5_single_gpu"] = n1
 
     if world == 1 and not args.no_extras and args.workload is None:
         # one record per remaining BASELINE config (fewer steps: they are not the headline)

@@ -79,6 +79,15 @@ int a2c_obs_ingest_rows_async(const uint8_t* frames_host, uint8_t* rows, long lo
 int a2c_obs_prep_stack_rows(const uint8_t* rows, const uint8_t* reset, uint8_t* planes,
                             uint8_t* pflag, int R, int F, int P, int j0, int layout, void* stream);
 
+/* The reference's other prep_fxn callables as batched device kernels (variants of the stage-1
+ * kernel for non-Pong environments), bit-identical to the numpy arithmetic:
+ *   kind 1  normalize_prep (a2c/preprocessing.py:4-6):  frames u8 [n,H,W,C] -> f64 [n,H,W,C]
+ *   kind 2  snake_prep     (a2c/preprocessing.py:25-32): frames u8 [n,H,W,C>=3] -> f32 [n,H,W]
+ *   kind 3  breakout_prep  (a2c/preprocessing.py:19-23): frames u8 [n,H>=195,W,C] -> u8 [n,80,(W-16+1)/2]
+ * (null_prep, :8-9, adds an axis and needs no kernel). */
+int a2c_prep_other(const uint8_t* frames, void* out, int kind, long long n_frames, int H, int W,
+                   int C, void* stream);
+
 /* Moves the last `fs` planes (+flags) of every slot to the head of its ring:
  * the bookmark state of a2c/runner.py:246. */
 int a2c_ring_carry(uint8_t* planes, uint8_t* pflag, int R, int P, int fs, void* stream);
@@ -219,21 +228,29 @@ int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
  * output whose ReLU gates dY. */
 int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
                         const a2c_conv_shape* s, int precision, void* stream);
-/* "Mask at the source" form used by a stack of Conv+ReLU layers (a2c/models.py:312,685): dY is
- * ALREADY masked by this layer's ReLU; X is this layer's input, i.e. the previous layer's ReLU
- * output.  dX = conv2d_transpose(dY) * (X > 0) is the previous layer's masked output gradient, and
- * dbias_prev f32 [Cin] (may be NULL) its bias gradient (per-channel sums of dX), both produced in
- * the epilogue of the input-gradient kernel: no backward kernel re-reads a forward output as a
- * mask and no separate bias-sum pass over dY exists.  workspace: >= 8*Cin bytes when dbias_prev. */
-int a2c_conv2d_bwd_data_relu(const float* dY, const float* Wt, const float* X, float* dX,
-                             float* dbias_prev, int N, const a2c_conv_shape* s, int precision,
-                             void* workspace, long long workspace_bytes, void* stream);
+/* "Mask at the source" form used by a stack of Conv+ReLU layers (a2c/models.py:312,685): X is
+ * this layer's input, i.e. the previous layer's ReLU output.  dX = conv2d_transpose(dY * (Ymask >
+ * 0)) * (X > 0) is the previous layer's MASKED output gradient and dbias_prev f32 [Cin] (may be
+ * NULL) its bias gradient (per-channel sums of dX), both produced in the epilogue of the
+ * input-gradient kernel: the previous layer's backward kernels then need no mask and no
+ * separate bias-sum pass over dY.  Ymask may be NULL (dY already masked).
+ * workspace: >= 8*Cin bytes when dbias_prev. */
+int a2c_conv2d_bwd_data_relu(const float* dY, const float* Ymask, const float* Wt, const float* X,
+                             float* dX, float* dbias_prev, int N, const a2c_conv_shape* s,
+                             int precision, void* workspace, long long workspace_bytes,
+                             void* stream);
 /* out f32 [C] = per-channel sums of X f32 [N, C, HW] where mask > 0 (mask may be NULL): the bias
  * gradient of the last conv layer from its masked output gradient.  workspace >= 8*C bytes. */
 int a2c_channel_sum(const float* X, const float* mask, float* out, int N, int C, int HW,
                     void* workspace, long long workspace_bytes, void* stream);
+/* Kernel family used by the last a2c_conv2d_* call of the calling host thread: 0 = tcgen05
+ * shift-GEMM, 1 = tcgen05 implicit GEMM over im2col tiles, 2 = fp32 FFMA direct convolution
+ * (-1: none yet).  Lets a host warn when a precision >= 1 request lands on the FFMA kernels. */
+int a2c_conv2d_last_path(void);
 /* Which backward entries apply the ReLU mask (Ymask > 0) themselves on the path they take for
- * this shape / precision: bit 0 = a2c_conv2d_bwd_data, bit 1 = a2c_conv2d_bwd_weight.  A caller
+ * this shape / precision: bit 0 = a2c_conv2d_bwd_data, bit 1 = a2c_conv2d_bwd_weight; bit 2 =
+ * a2c_conv2d_bwd_weight also yields dbias at no extra cost on that path (otherwise a non-NULL
+ * dbias costs a separate pass over dY).  A caller
  * holding an unmasked dY passes Ymask to those and pre-masks dY (a2c_relu_bwd) for the others;
  * passing Ymask to an entry whose bit is clear is still correct but runs the fp32 FFMA kernel. */
 int a2c_conv2d_fused_mask(const a2c_conv_shape* s, int precision, int input_is_view);
@@ -244,6 +261,20 @@ int a2c_conv2d_bwd_weight(const float* X, const a2c_state_view* xview, const flo
                           const float* Ymask, float* dW, float* dbias, int N,
                           const a2c_conv_shape* s, void* workspace, long long workspace_bytes,
                           int precision, void* stream);
+
+/* Explicit patch matrices for convolutions without a shift-GEMM form (A3CModel's 8x8 s4 and
+ * 4x4 s2 layers, a2c/models.py:22-38): col f32 [N*OH*OW, Cin*K*K] is written once and the layer's
+ * forward / weight gradient / input gradient run as a2c_gemm on it.  Exactly one source:
+ *   xview   planar states (uint8 ring or f32), column order k = (ci*K + ky)*K + kx  (the
+ *           reference's W.view(Cout, -1) as is); needs K % 4 == 0;
+ *   x_nhwc  channels-last f32 [N, H, W, Cin] (the GEMM output of the previous such layer), column
+ *           order k = (ky*K + kx)*Cin + ci; needs Cin % 4 == 0.
+ * a2c_col2im_nhwc: dX [N, H, W, Cin] = gather of dcol (channels-fastest order), gated by
+ * xmask > 0 (channels-last like dX; may be NULL). */
+int a2c_im2col(const a2c_state_view* xview, const float* x_nhwc, float* col, int N,
+               const a2c_conv_shape* s, void* stream);
+int a2c_col2im_nhwc(const float* dcol, const float* xmask, float* dx, int N,
+                    const a2c_conv_shape* s, void* stream);
 
 /* LayerNorm over the last dim (eps 1e-5), rows x H.  Saves mean / rstd f32 [rows]. */
 int a2c_layernorm_fwd(const float* X, const float* gamma, const float* beta, float* Y,

@@ -43,6 +43,36 @@ def pong_prep(pic):
     return out[None]
 
 
+def normalize_prep(pic):
+    """a2c/preprocessing.py:4-6."""
+    new_pic = 3 * (pic - 255 / 2) / (255 / 2)
+    return new_pic[None]
+
+
+def null_prep(pic):
+    """a2c/preprocessing.py:8-9."""
+    return pic[None]
+
+
+def breakout_prep(pic):
+    """a2c/preprocessing.py:19-23.  ``rgb2grey`` of the 2-D channel-0 array is the identity in
+    the skimage releases that still export that name (rgb2gray returned 2-D input unchanged
+    until it was removed); skimage is not installed here, so this step is restated, not run."""
+    pic = pic[35:195, 8:-8]
+    pic = pic[::2, ::2, 0]
+    return np.ascontiguousarray(pic)[None]
+
+
+def snake_prep(pic):
+    """a2c/preprocessing.py:25-32."""
+    new_pic = np.zeros(pic.shape[:2], dtype=np.float32)
+    new_pic[:, :][pic[:, :, 0] == 1] = 1
+    new_pic[:, :][pic[:, :, 0] == 255] = 1.5
+    new_pic[:, :][pic[:, :, 1] == 255] = 0
+    new_pic[:, :][pic[:, :, 2] == 255] = .33
+    return new_pic[None]
+
+
 class FrameStack:
     """a2c/utils.py:26-43 (``next_state``) with its ``deque(maxlen=fs)``
     (a2c/runner.py:145).  On reset: fs-1 zero planes then the reset

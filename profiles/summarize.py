@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Summarise ncu captures into the small text files kept under profiles/.
 
-  python profiles/summarize.py full  <report.ncu-rep> <out.md>   # one `--set full` capture
-  python profiles/summarize.py list  <launches.csv>   <out.md>   # a gpu__time_duration launch list
+  python profiles/summarize.py full     <report.ncu-rep> <out.md>   # one `--set full` capture
+  python profiles/summarize.py fullcsv  <raw.csv>        <out.md>   # the same from `ncu -i rep --page raw --csv`
+                                                                    # (what travels back from the GPU box: < 64 MB)
+  python profiles/summarize.py list     <launches.csv>   <out.md>   # a gpu__time_duration launch list
 
 The .ncu-rep files themselves stay in gpurun_out/ (scratch, not tracked).
 """
@@ -21,15 +23,22 @@ KEYS = [
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "sm__inst_executed.sum", "sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_lsu.sum",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
 ]
 
 
-def full(rep, out):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
+def full(rep, out, from_csv=False):
+    if from_csv:
+        txt = open(rep, errors="replace").read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units = rows[0], rows[1]
     lines = ["# ncu --set full summary of %s" % rep.split("/")[-1], ""]
@@ -85,4 +94,4 @@ def launch_list(path, out):
 
 
 if __name__ == "__main__":
-    {"full": full, "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"full": full, "fullcsv": lambda a, b: full(a, b, True), "list": launch_list}[sys.argv[1]](sys.argv[2], sys.argv[3])

@@ -54,6 +54,7 @@ SIGNATURES = {
     "a2c_obs_ingest_bytes_per_frame": [_i],
     "a2c_obs_ingest_rows_async": [_p, _p, _ll, _i, _p],
     "a2c_obs_prep_stack_rows": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "a2c_prep_other": [_p, _p, _i, _ll, _i, _i, _i, _p],
     "a2c_ring_carry": [_p, _p, _i, _i, _i, _p],
     "a2c_states_materialize": [_SV, _p, _i, _i, _p],
     "a2c_sample_action": [_p, _p, _p, _i, _i, _i, _p],
@@ -69,11 +70,14 @@ SIGNATURES = {
     "a2c_relu_bwd": [_p, _p, _p, _ll, _p],
     "a2c_conv2d_fwd": [_p, _SV, _p, _p, _p, _i, _CS, _i, _i, _p],
     "a2c_conv2d_bwd_data": [_p, _p, _p, _p, _i, _CS, _i, _p],
-    "a2c_conv2d_bwd_data_relu": [_p, _p, _p, _p, _p, _i, _CS, _i, _p, _ll, _p],
+    "a2c_conv2d_bwd_data_relu": [_p, _p, _p, _p, _p, _p, _i, _CS, _i, _p, _ll, _p],
     "a2c_channel_sum": [_p, _p, _p, _i, _i, _i, _p, _ll, _p],
+    "a2c_conv2d_last_path": [],
     "a2c_conv2d_fused_mask": [_CS, _i, _i],
     "a2c_conv2d_bwd_weight_workspace": [_CS],
     "a2c_conv2d_bwd_weight": [_p, _SV, _p, _p, _p, _p, _i, _CS, _p, _ll, _i, _p],
+    "a2c_im2col": [_SV, _p, _p, _i, _CS, _p],
+    "a2c_col2im_nhwc": [_p, _p, _p, _i, _CS, _p],
     "a2c_layernorm_fwd": [_p, _p, _p, _p, _p, _p, _ll, _i, _p],
     "a2c_layernorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _ll, _i, _p],
     "a2c_gru_gates1": [_p, _p, _p, _p, _p, _p, _ll, _i, _p],
@@ -87,7 +91,7 @@ _RESTYPES = {"a2c_last_error": C.c_char_p, "a2c_launch_count": C.c_longlong,
              "a2c_obs_ingest_bytes_per_frame": C.c_longlong,
              "a2c_conv2d_bwd_weight_workspace": C.c_longlong}
 _NO_STATUS = {"a2c_abi_version", "a2c_last_error", "a2c_launch_count", "a2c_obs_ingest_bytes_per_frame",
-              "a2c_conv2d_bwd_weight_workspace", "a2c_conv2d_fused_mask"}
+              "a2c_conv2d_bwd_weight_workspace", "a2c_conv2d_fused_mask", "a2c_conv2d_last_path"}
 
 _lib = None
 

@@ -16,7 +16,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .ops import ConvStackFn, GRUCellFn, GRUSequenceFn, LayerNormFn, LinearFn, LinearStateFn, View
+from .ops import (ConvStackFn, GRUCellFn, GRUSequenceFn, Im2colStackFn, LayerNormFn, LinearFn, LinearStateFn,
+                  View, nhwc_linear_weight)
 
 
 def _as_view(x):
@@ -138,7 +139,19 @@ class A3CModel(_PolicyBase):
         self.value = nn.Linear(h_size, 1)
 
     def encoder(self, state):
-        return _linear(self._features(_as_view(state)), self.proj_matrx, x_relu=True)
+        view = _as_view(state)
+        if ops.get_precision() >= 1:
+            # 8x8 s4 / 4x4 s2 layers have no shift-GEMM form: explicit patch matrices + tcgen05 GEMMs,
+            # activations channels-last; the projection weight is permuted instead of the activations
+            geom = tuple((blk[0].stride[0], blk[0].padding[0]) for blk in self.convs)
+            params = []
+            for blk in self.convs:
+                params += [blk[0].weight, blk[0].bias]
+            feats = Im2colStackFn.apply(view, geom, *params)
+            cout = self.convs[-1][0].out_channels
+            w = nhwc_linear_weight(self.proj_matrx.weight, cout, self.flat_size // cout)
+            return LinearFn.apply(feats, w, self.proj_matrx.bias, False, True)
+        return _linear(self._features(view), self.proj_matrx, x_relu=True)
 
     def policy(self, state_emb, bnorm=False):
         if bnorm:

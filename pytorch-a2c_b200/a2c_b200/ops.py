@@ -169,12 +169,13 @@ class FrameIngest:
     pinned host memory into a device staging buffer, so it runs under the previous update's
     kernels; ``commit(ring)`` makes the compute stream wait for that copy and runs stage 1 from
     the staging buffer.  ``layout`` picks what crosses PCIe (see a2c_obs_ingest_rows_async):
-    0 = only the 80 selected rows of each frame (38 % of the bytes, 480-byte DMA rows), 1 = the
-    cropped band of each frame (76 %, one 76 KB run per frame), 2 = whole frames.  ``depth``
+    0 = only the 80 selected rows of each frame (38 % of the bytes, 480-byte DMA rows: 49 GB/s
+    measured, the default -- least time on the link, which bounds configs like C3), 1 = the
+    cropped band of each frame (76 %, one 76 KB run per frame, 55 GB/s), 2 = whole frames.  ``depth``
     staging buffers are cycled; a buffer is overwritten only after the stage-1 launch that read
     it has finished (event on the compute stream)."""
 
-    def __init__(self, R, F, device, depth=2, layout=1):
+    def __init__(self, R, F, device, depth=2, layout=0):
         self.R, self.F, self.device, self.layout = R, F, device, layout
         self.stream = torch.cuda.Stream(device=device)
         self.frame_bytes = int(call("a2c_obs_ingest_bytes_per_frame", layout))
@@ -405,6 +406,18 @@ class LinearStateFn(torch.autograd.Function):
         return None, dW, db, None
 
 
+_SLOW_PATH_WARNED = set()
+
+
+def _warn_if_ffma(op, sig, precision):
+    """One warning per (op, layer shape) when a tensor-core request ran on the FFMA kernels."""
+    if precision >= 1 and (op, sig) not in _SLOW_PATH_WARNED and call("a2c_conv2d_last_path") == 2:
+        _SLOW_PATH_WARNED.add((op, sig))
+        import warnings
+        warnings.warn("a2c_b200: %s of conv layer %s has no tcgen05 path at precision %d and ran on the "
+                      "fp32 FFMA kernels" % (op, sig, precision), RuntimeWarning, stacklevel=3)
+
+
 def conv_shape(Cin, Cout, H, W, K, stride, pad):
     OH = (H - K + 2 * pad) // stride + 1
     OW = (W - K + 2 * pad) // stride + 1
@@ -521,6 +534,7 @@ class ConvStackFn(torch.autograd.Function):
             call("a2c_conv2d_fwd", None if first_view else ptr(cur), C.byref(cur.c) if first_view else None,
                  ptr(W), ptr(b), ptr(y), N, C.byref(s), 1, _PRECISION, stream_ptr(),
                  tag="a2c_conv2d_fwd|flops|" + sig, work=flops)
+            _warn_if_ffma("forward", sig, _PRECISION)
             shapes.append((s, flops, sig))
             acts.append(y)
             cur = y
@@ -542,38 +556,152 @@ class ConvStackFn(torch.autograd.Function):
         dev = dy.device
         grads = [None] * (2 * L)
         ws0 = workspace(dev)
-        # bias gradient of the last layer: channel sums of its masked output gradient
-        sL = ctx.shapes[-1][0]
-        db = torch.empty(sL.Cout, dtype=torch.float32, device=dev)
-        call("a2c_channel_sum", ptr(dy), None, ptr(db), N, sL.Cout, sL.OH * sL.OW, ptr(ws0), ws0.numel(),
-             stream_ptr())
-        grads[2 * (L - 1) + 1] = db
+        # Where is each ReLU mask applied?  Boundary l | l+1 (layer l's output gradient):
+        #   at the source  -- layer l+1's input-gradient epilogue writes the masked gradient and its
+        #                     channel sums (= layer l's bias gradient); costs one strided read of Y_l there;
+        #   in the consumers -- layer l's weight- and input-gradient producers read Y_l as a mask.
+        # Measured on B200: the source form wins exactly when layer l would
+        # otherwise need a separate bias-sum pass over dY (its weight-gradient kernel has no free
+        # operand slot for the bias row), so that is the rule.
+        free_bias = []
+        for l in range(L):
+            s = ctx.shapes[l][0]
+            bits = call("a2c_conv2d_fused_mask", C.byref(s), prec, 1 if (l == 0 and ctx.is_view) else 0)
+            free_bias.append(bool(bits & 4))
+        masked = True                   # is `dy` (layer l's output gradient) already masked?
+        have_bias = False               # has layer l's bias gradient been produced by the layer above?
         dx0 = None
         for l in range(L - 1, -1, -1):
             s, flops, sig = ctx.shapes[l]
             W = Ws[l]
             xin = acts[l - 1] if l > 0 else x0
-            # weight gradient (bias gradients come from the epilogues above / the channel sum)
+            mask = None if masked else acts[l]
+            db = None
+            if not have_bias:
+                db = torch.empty(s.Cout, dtype=torch.float32, device=dev)
+                if masked and not free_bias[l]:
+                    # top layer without a free slot: channel sums of its (masked) output gradient
+                    call("a2c_channel_sum", ptr(dy), None, ptr(db), N, s.Cout, s.OH * s.OW, ptr(ws0),
+                         ws0.numel(), stream_ptr())
+                    grads[2 * l + 1], db = db, None
+                else:
+                    grads[2 * l + 1] = db          # written by the weight-gradient call below
             dW = torch.empty_like(W)
             need = call("a2c_conv2d_bwd_weight_workspace", C.byref(s))
             ws = workspace(dev, max(need, 64 << 20))
             first_view = l == 0 and ctx.is_view
             call("a2c_conv2d_bwd_weight", None if first_view else ptr(xin),
-                 C.byref(ctx.view.c) if first_view else None, ptr(dy), None, ptr(dW), None, N, C.byref(s),
-                 ptr(ws), ws.numel(), prec, stream_ptr(), tag="a2c_conv2d_bwd_weight|flops|" + sig, work=flops)
+                 C.byref(ctx.view.c) if first_view else None, ptr(dy), ptr(mask), ptr(dW), ptr(db), N,
+                 C.byref(s), ptr(ws), ws.numel(), prec, stream_ptr(),
+                 tag="a2c_conv2d_bwd_weight|flops|" + sig, work=flops)
+            _warn_if_ffma("weight gradient", sig, prec)
             grads[2 * l] = dW
             if l > 0:
                 dx = torch.empty_like(xin)
-                dbp = torch.empty(s.Cin, dtype=torch.float32, device=dev)
-                call("a2c_conv2d_bwd_data_relu", ptr(dy), ptr(W), ptr(xin), ptr(dx), ptr(dbp), N, C.byref(s),
-                     prec, ptr(ws), ws.numel(), stream_ptr(), tag="a2c_conv2d_bwd_data|flops|" + sig, work=flops)
-                grads[2 * (l - 1) + 1] = dbp
+                at_source = not free_bias[l - 1]
+                if at_source:
+                    dbp = torch.empty(s.Cin, dtype=torch.float32, device=dev)
+                    call("a2c_conv2d_bwd_data_relu", ptr(dy), ptr(mask), ptr(W), ptr(xin), ptr(dx), ptr(dbp), N,
+                         C.byref(s), prec, ptr(ws), ws.numel(), stream_ptr(),
+                         tag="a2c_conv2d_bwd_data|flops|" + sig, work=flops)
+                    grads[2 * (l - 1) + 1] = dbp
+                else:
+                    call("a2c_conv2d_bwd_data", ptr(dy), ptr(mask), ptr(W), ptr(dx), N, C.byref(s), prec,
+                         stream_ptr(), tag="a2c_conv2d_bwd_data|flops|" + sig, work=flops)
+                masked, have_bias = at_source, at_source
                 dy = dx
             elif not ctx.is_view and ctx.needs_input_grad[0]:
                 dx0 = torch.empty_like(x0)
-                call("a2c_conv2d_bwd_data", ptr(dy), None, ptr(W), ptr(dx0), N, C.byref(s), prec, stream_ptr(),
-                     tag="a2c_conv2d_bwd_data|flops|" + sig, work=flops)
+                call("a2c_conv2d_bwd_data", ptr(dy), ptr(mask), ptr(W), ptr(dx0), N, C.byref(s), prec,
+                     stream_ptr(), tag="a2c_conv2d_bwd_data|flops|" + sig, work=flops)
         return (dx0, None, None) + tuple(grads)
+
+
+class Im2colStackFn(torch.autograd.Function):
+    """Conv2d + ReLU stack for layers without a shift-GEMM form (A3CModel's 8x8 s4 and 4x4 s2
+    convolutions, a2c/models.py:22-38, 98) as ONE autograd node on explicit patch matrices:
+
+        col_l = im2col(input_l)             [N*OH*OW, Cin*K*K]   written to HBM once, kept for backward
+        Y_l   = relu(col_l W_l^T + b_l)     [N*OH*OW, Cout]      channels-last = the next layer's input
+        dW_l  = (col_l^T dY_l)^T            split-K tcgen05 GEMM over the N*OH*OW rows
+        dY_{l-1} = col2im(dY_l W_l) * (Y_{l-1} > 0)
+
+    Every contraction is a2c_gemm (3xTF32 on tcgen05 at precision 1); the layers are HBM-bound on
+    the patch-matrix traffic.  The first layer reads the state view (uint8 ring) with the
+    reference's weight flattening; later layers use channels-fastest columns and a permuted copy
+    of the (tiny) weight.  Returns the last activation FLATTENED CHANNELS-LAST, [N, OH*OW*Cout]:
+    the caller permutes the weight of the Linear layer that follows (``nhwc_linear_weight``)
+    instead of transposing the activations.  The incoming gradient must already be masked by the
+    last ReLU (LinearFn(..., x_relu=True) does that in its input-gradient GEMM)."""
+
+    @staticmethod
+    def forward(ctx, view, geom, *params):
+        L = len(geom)
+        assert isinstance(view, View) and len(params) == 2 * L
+        dev = params[0].device
+        N = view.N
+        cols, acts, shapes, wflat = [], [], [], []
+        Hh = Ww = 80
+        cur = None
+        for l in range(L):
+            W, b = params[2 * l], params[2 * l + 1]
+            require_cuda(W, b)
+            Cout, Cin, K, _ = W.shape
+            stride, pad = geom[l]
+            s = conv_shape(Cin, Cout, Hh, Ww, K, stride, pad)
+            Kc = Cin * K * K
+            M = N * s.OH * s.OW
+            col = torch.empty((M, Kc), dtype=torch.float32, device=dev)
+            if l == 0:
+                assert view.fs == Cin
+                call("a2c_im2col", C.byref(view.c), None, ptr(col), N, C.byref(s), stream_ptr(),
+                     tag="a2c_im2col|bytes|%d:%d,k%ds%d" % (N, Cin, K, stride), work=4.0 * M * Kc)
+                wf = W.reshape(Cout, Kc)                       # k = (ci, ky, kx): the reference's order
+            else:
+                call("a2c_im2col", None, ptr(cur), ptr(col), N, C.byref(s), stream_ptr(),
+                     tag="a2c_im2col|bytes|%d:%d,k%ds%d" % (N, Cin, K, stride), work=8.0 * M * Kc)
+                wf = W.permute(0, 2, 3, 1).reshape(Cout, Kc).contiguous()     # k = (ky, kx, ci)
+            y = gemm(col, Kc, 1, wf, 1, Kc, M, Cout, Kc, bias=b, relu=True)    # [M, Cout] channels-last
+            cols.append(col); acts.append(y); shapes.append(s); wflat.append(wf)
+            cur, Hh, Ww = y, s.OH, s.OW
+        ctx.shapes, ctx.N, ctx.L = shapes, N, L
+        ctx.save_for_backward(*(cols + acts + wflat))
+        return acts[-1].view(N, -1)
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        L, N = ctx.L, ctx.N
+        saved = ctx.saved_tensors
+        cols, acts, wflat = saved[:L], saved[L:2 * L], saved[2 * L:]
+        dev = dfeat.device
+        grads = [None] * (2 * L)
+        dy = dfeat.contiguous().view(acts[-1].shape)           # already masked by the last ReLU
+        for l in range(L - 1, -1, -1):
+            s = ctx.shapes[l]
+            Kc = s.Cin * s.K * s.K
+            M = N * s.OH * s.OW
+            # dW^T [Kc, Cout] = col^T dY  (few output tiles, K = M rows: split-K)
+            dWt = gemm(cols[l], 1, Kc, dy, s.Cout, 1, Kc, s.Cout, M)
+            if l == 0:
+                grads[0] = dWt.t().reshape(s.Cout, s.Cin, s.K, s.K)
+            else:
+                grads[2 * l] = dWt.t().reshape(s.Cout, s.K, s.K, s.Cin).permute(0, 3, 1, 2)
+            grads[2 * l + 1] = colsum(dy, M, s.Cout)
+            if l > 0:
+                dcol = gemm(dy, s.Cout, 1, wflat[l], Kc, 1, M, Kc, s.Cout)     # dY W  [M, Kc], channels fastest
+                dx = torch.empty_like(acts[l - 1])
+                call("a2c_col2im_nhwc", ptr(dcol), ptr(acts[l - 1]), ptr(dx), N, C.byref(s), stream_ptr(),
+                     tag="a2c_col2im|bytes|%d:%d,k%ds%d" % (N, s.Cin, s.K, s.stride), work=4.0 * M * Kc)
+                dy = dx
+        return (None, None) + tuple(grads)
+
+
+def nhwc_linear_weight(W, C_, P_):
+    """Weight of a Linear layer that follows a channels-last flatten: column (pos*C + c) of the
+    result is column (c*P + pos) of the reference-layout weight [out, C*P] (differentiable view ops;
+    the parameter itself keeps the reference layout, so checkpoints interchange)."""
+    out = W.shape[0]
+    return W.view(out, C_, P_).transpose(1, 2).reshape(out, P_ * C_)
 
 
 class LayerNormFn(torch.autograd.Function):

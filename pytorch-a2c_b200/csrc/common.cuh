@@ -93,6 +93,13 @@ __device__ __forceinline__ T block_sum(T v, T* scratch) {
   return v;
 }
 
+// Asks L2 for the 128-byte line holding p (no register result, no scoreboard): the producers of the
+// convolution kernels call it one work item ahead, so that the loads of the item they convert next
+// find their data in L2 instead of paying HBM latency inside the wait -> load -> store -> MMA chain.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -234,9 +234,30 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
     const bool lane_on = sub < tpw;
     const int plane = p.SH * p.SW;                             // elements per channel
     StageRing ring(p.nbuf);
+    // L2 prefetch of a band's source rows (and mask rows), one item ahead, spread over the producer lanes
+    auto prefetch_band = [&](int nitem) {
+      if (FIRST || p.use_view) return;                      // the uint8 ring is 1/6400th of the traffic
+      const BandInfo nb = band_info(p, nitem);
+      const int sy0 = nb.r0 * p.cs - p.p0y;
+      const int nrow = (nb.rows + p.rext_y[0]) * p.cs;
+      const int lines = (p.SW * 4 + 127) >> 7;               // 128-byte lines per source row (+1 when unaligned)
+      const int nseg = nrow * p.C * (lines + 1);
+      for (int sg = warp * 32 + lane; sg < nseg; sg += SH_PROD * 32) {
+        const int ln = sg % (lines + 1);
+        const int rc = sg / (lines + 1);
+        const int r = rc / p.C, c = rc - r * p.C;
+        const int sy = sy0 + r;
+        if ((unsigned)sy >= (unsigned)p.SH) continue;
+        const long long off = ((long long)nb.img * p.C + c) * plane + sy * p.SW + min(ln * 32, p.SW - 1);
+        prefetch_l2(p.src + off);
+        if (p.mask) prefetch_l2(p.mask + off);
+      }
+    };
+    if ((int)blockIdx.x < nitems) prefetch_band(blockIdx.x);
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, ring.next()) {
       const BandInfo bd = band_info(p, item);
       uint8_t* buf = bufs + (size_t)ring.s * p.buf_bytes;
+      if (item + (int)gridDim.x < nitems) prefetch_band(item + gridDim.x);
       mbar_wait_relaxed(&patch_empty[ring.s], ring.par ^ 1);   // long wait: do not burn issue slots
       const float4* simg = reinterpret_cast<const float4*>(p.src + (long long)bd.img * p.C * plane);
       // first layers: element offset of channel 0, channel stride and live-plane mask of this image
@@ -437,6 +458,19 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
           const int idx0 = (j * p.os + c.a) * p.OutW + i * p.os + c.b;
           float mk[MASKOUT ? NCOL : 1];
           if constexpr (MASKOUT) {
+            // the NEXT tile's mask lines go to L2 now (no registers held), so that its loads below hit L2:
+            // the drain handles tiles one after the other and would otherwise pay HBM latency per tile
+            {
+              int jn = jr + q128, in_ = i + r128;
+              if (in_ >= p.PW) { in_ -= p.PW; ++jn; }
+              const int j2 = bd.r0 + jn;
+              if (t + 1 < bd.ntile && jn < bd.rows && j2 < c.qh && in_ < c.qw) {
+                const float* a = mimg + (j2 * p.os + c.a) * p.OutW + in_ * p.os + c.b;
+#pragma unroll
+                for (int jj = 0; jj < NCOL; ++jj)
+                  if (jj < nvalid) prefetch_l2(a + jj * plane);
+              }
+            }
 #pragma unroll
             for (int jj = 0; jj < NCOL; ++jj)
               mk[jj] = (pvalid && jj < nvalid) ? __ldg(mimg + idx0 + jj * plane) : 0.0f;

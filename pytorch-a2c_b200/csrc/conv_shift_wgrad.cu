@@ -67,6 +67,7 @@ struct WgShiftParams {
   int N, Cin, H, W, Cout, OH, OW;   // Cin: input channels of THIS launch (a chunk of <= 32 of CinTot)
   int CinTot, ci0;       // channels per image of x, first channel of this launch
   int scalar_w;          // W or OW not a multiple of 4 (10x10 / 5x5 planes): one pixel per lane, scalar loads
+  int opack;             // Cout <= 16: a dY row holds [hi (16 slots) | lo (16 slots)] in ONE 32-slot atom, no second copy
   int S;                 // stride
   int pack2;             // stride 1, Cin <= 16: slots [16,32) = channels of the next image row
   int ncx;               // x-parity planes per X row (1, or 2 for stride 2)
@@ -103,6 +104,19 @@ __device__ __forceinline__ void wg_store_split(uint8_t* dst, int half_bytes, flo
   const float4 h = make_float4(tf32_rna(a), tf32_rna(b), tf32_rna(c), tf32_rna(d));
   *reinterpret_cast<float4*>(dst) = h;
   *reinterpret_cast<float4*>(dst + half_bytes) = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);
+}
+
+// Stores the hi / lo split of 4 channels (16-byte chunk `cg` of a dY position row).  Unpacked: the lo copy
+// lives o_half bytes after the hi copy.  Packed (Cout <= 16): it is chunk cg + 4 of the SAME row.
+__device__ __forceinline__ void wg_store_dy(uint8_t* buf, uint32_t pos, uint32_t cg, int o_half, int opack,
+                                            float a, float b, float c, float d) {
+  const uint32_t c16 = (cg & 1u) << 4, c32 = cg >> 1;
+  uint8_t* row = buf + pos * 128u;
+  uint8_t* hi = row + (((c32 ^ (pos & 3u)) << 5) | c16);
+  uint8_t* lo = opack ? row + ((((c32 + 2u) ^ (pos & 3u)) << 5) | c16) : hi + o_half;
+  const float4 h = make_float4(tf32_rna(a), tf32_rna(b), tf32_rna(c), tf32_rna(d));
+  *reinterpret_cast<float4*>(hi) = h;
+  *reinterpret_cast<float4*>(lo) = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);
 }
 
 __device__ __forceinline__ void wg_tmem_ld16(uint32_t taddr, uint32_t* r) {
@@ -405,9 +419,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
             if (mimg) v = __ldg(mimg + a) > 0.f ? v : 0.f;
             c4[c] = v;
           }
-          const uint32_t pos = (uint32_t)(jj * p.PWo + xo);
-          const uint32_t c16 = ((uint32_t)cg & 1u) << 4, c32 = (uint32_t)cg >> 1;
-          wg_store_split(buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16), p.o_half, c4[0], c4[1], c4[2], c4[3]);
+          wg_store_dy(buf, (uint32_t)(jj * p.PWo + xo), (uint32_t)cg, p.o_half, p.opack, c4[0], c4[1], c4[2], c4[3]);
         }
       } else {
         uint8_t* buf = ob + (size_t)ring.s * p.o_buf;
@@ -436,13 +448,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
           const float px[4][4] = {{v0.x, v1.x, v2.x, v3.x}, {v0.y, v1.y, v2.y, v3.y},
                                   {v0.z, v1.z, v2.z, v3.z}, {v0.w, v1.w, v2.w, v3.w}};
           const uint32_t pos0 = (uint32_t)(jj * p.PWo + 4 * gio);
-          const uint32_t c16 = ((uint32_t)cg & 1u) << 4, c32 = (uint32_t)cg >> 1;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t pos = pos0 + (uint32_t)((j + gio) & 3);
-            uint8_t* d = buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16);
-            wg_store_split(d, p.o_half, px[j][0], px[j][1], px[j][2], px[j][3]);
-          }
+          for (int j = 0; j < 4; ++j)
+            wg_store_dy(buf, pos0 + (uint32_t)((j + gio) & 3), (uint32_t)cg, p.o_half, p.opack, px[j][0], px[j][1],
+                        px[j][2], px[j][3]);
         }
       }
       }
@@ -483,9 +492,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
           const uint32_t tmem_d = tmem_base + ab * WG_TCOLS;
           const int j1 = min(it.rows, j0 + p.rpc);
           // idesc / descriptor high word as immediates (uniform-register issue loop, see mma_tf32_imm)
-          auto issue = [&](auto mtag) {
-            constexpr uint32_t ID1 = make_idesc_mn(decltype(mtag)::value, WG_N);        // X_lo * dY_hi
-            constexpr uint32_t ID2 = make_idesc_mn(decltype(mtag)::value, 2 * WG_N);    // X_hi * [dY_hi | dY_lo]
+          auto issue = [&](auto mtag, auto ntag) {
+            constexpr int NH = decltype(ntag)::value;                                   // dY_hi columns: 32, or 16 when packed
+            constexpr uint32_t ID1 = make_idesc_mn(decltype(mtag)::value, NH);          // X_lo * dY_hi
+            constexpr uint32_t ID2 = make_idesc_mn(decltype(mtag)::value, 2 * NH);      // X_hi * [dY_hi | dY_lo]
             uint32_t acc = 0;
             for (int jj = j0; jj < j1; ++jj) {
               uint32_t a_row = a_buf + (uint32_t)jj * xrow16;
@@ -497,9 +507,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
                   const uint32_t a_hi = a_row + (p.ncx == 1 ? (uint32_t)kx : (uint32_t)((kx & 1) * p.PWx + (kx >> 1))) * 8u;
                   // (measured: the swizzle phase comes from the absolute address bits, so a start that is
                   //  not aligned to the 512-byte pattern needs NO base offset in the descriptor)
-                  mma_tf32_imm<ID2, WG_DESC_HI>(tmem_d + kx * 2 * WG_N, a_hi, b_row, acc);
+                  mma_tf32_imm<ID2, WG_DESC_HI>(tmem_d + kx * 2 * NH, a_hi, b_row, acc);
                   // ({0,1} ring sources are exact in TF32: no X_lo term)
-                  if (p.nsplit == 2) mma_tf32_imm<ID1, WG_DESC_HI>(tmem_d + kx * 2 * WG_N, a_hi + xhalf16, b_row, 1u);
+                  if (p.nsplit == 2) mma_tf32_imm<ID1, WG_DESC_HI>(tmem_d + kx * 2 * NH, a_hi + xhalf16, b_row, 1u);
                 }
                 acc = 1u;
                 a_row += 8 * 8;
@@ -507,8 +517,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
               }
             }
           };
-          if (p.mrows == 64) issue(std::integral_constant<int, 64>{});
-          else issue(std::integral_constant<int, 128>{});
+          if (p.opack) {
+            if (p.mrows == 64) issue(std::integral_constant<int, 64>{}, std::integral_constant<int, 16>{});
+            else issue(std::integral_constant<int, 128>{}, std::integral_constant<int, 16>{});
+          } else {
+            if (p.mrows == 64) issue(std::integral_constant<int, 64>{}, std::integral_constant<int, 32>{});
+            else issue(std::integral_constant<int, 128>{}, std::integral_constant<int, 32>{});
+          }
         }
         __syncwarp();
         if (elect_one()) mma_commit(&acc_full[ab]);
@@ -534,11 +549,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         for (int c0 = 0; c0 < NC; c0 += 8) {
           // output (kx, co) = hsel * NC + c0 + j  lives in TMEM columns kx * 64 + co (and + 32 for the dy_lo
           // half); 8 columns at a time keeps the 48 running sums + both halves inside the register budget
+          // (packed dY, Cout <= 16: per kx [hi 16 | lo 16]; outputs co >= 16 are never read by the reduction)
           const int o = hsel * NC + c0;
-          const uint32_t col = (uint32_t)((o / WG_N) * 2 * WG_N + (o % WG_N));
+          const uint32_t nh = p.opack ? 16u : (uint32_t)WG_N;
+          const uint32_t col = (uint32_t)(o / WG_N) * 2u * nh + (uint32_t)(o % WG_N);
           uint32_t r[8], r2[8];
           wg_tmem_ld8(taddr + col, r);
-          wg_tmem_ld8(taddr + col + WG_N, r2);
+          wg_tmem_ld8(taddr + col + nh, r2);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[c0 + j] += __uint_as_float(r[j]) + __uint_as_float(r2[j]);
@@ -647,8 +664,9 @@ static bool wg_plan(WgShiftParams* p) {
     // every hi / lo copy and buffer stays 1024-byte aligned (the swizzle phase is taken from address bits)
     const long long xh = ((long long)p->xrows * p->ncx * p->PWx * WG_ROWB + 1023) & ~1023LL;
     const long long oh = ((long long)p->Rb * p->PWo * WG_ROWB + 1023) & ~1023LL;
-    p->x_half = (int)xh; p->x_buf = (int)(2 * xh);
-    p->o_half = (int)oh; p->o_buf = (int)(2 * oh);
+    // (sources that are exact in TF32 have no lo copy; packed dY rows hold hi and lo side by side)
+    p->x_half = (int)xh; p->x_buf = (int)((p->nsplit == 2 ? 2 : 1) * xh);
+    p->o_half = (int)oh; p->o_buf = (int)((p->opack ? 1 : 2) * oh);
     if (wg_smem_bytes(*p) <= (size_t)WG_SMEM_LIMIT) return true;
   }
   return false;
@@ -692,6 +710,18 @@ bool conv_wgrad_shift_ok(const a2c_conv_shape* s) {
   return !(first && scalar);
 }
 
+// true when the shift-GEMM weight gradient of this layer also yields the bias gradient at no extra cost
+// (a free 4-slot chunk of the X rows carries the constant 1, see ones_chunk below)
+bool conv_wgrad_shift_bias_free(const a2c_conv_shape* s) {
+  if (!conv_wgrad_shift_ok(s)) return false;
+  const bool first = s->Cin <= 4 && s->stride == 1;
+  if (first) return true;
+  if (s->stride == 1 && s->Cin <= 16) return false;            // pack2: both 16-slot halves carry channels
+  for (int ci0 = 0; ci0 < s->Cin; ci0 += 32)
+    if ((s->Cin - ci0 < 32 ? s->Cin - ci0 : 32) <= 28) return true;
+  return false;
+}
+
 // 0 = ran, 1 = not supported (caller falls back), else error
 int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const float* dY, const float* Ymask,
                          float* dW, float* dbias, int N, const a2c_conv_shape* s, void* workspace,
@@ -725,6 +755,7 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   p.pack3 = first ? 1 : 0;
   { const int np = first ? 1 : (cin / 4 + 1) / 2; p.inv_ncgx = (65536 + np - 1) / np; }
   p.nsplit = xview ? 1 : 2;
+  p.opack = s->Cout <= 16 ? 1 : 0;
   p.Cout = s->Cout; p.OH = s->OH; p.OW = s->OW; p.S = S; p.ncx = S;
   p.OWc = owc;
   p.ncol = s->OW / owc;

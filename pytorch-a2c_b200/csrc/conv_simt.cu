@@ -428,6 +428,20 @@ static int launch_wgrad_t(ConvWgParams p, const WgPlan& pl, int wsize, float* dW
   return 0;
 }
 
+// Which kernel family the last a2c_conv2d_* call of this host thread used:
+// 0 = tcgen05 shift-GEMM, 1 = tcgen05 implicit GEMM (im2col tiles), 2 = fp32 FFMA.  The host layer
+// warns once per layer shape when a precision >= 1 request ends on the FFMA kernels (a shape that
+// misses every tensor-core path would otherwise be a silent 5-10x slowdown).
+static thread_local int g_last_path = -1;
+#define A2C_PATH_RETURN(path, rc_expr) \
+  do {                                   \
+    int rc__ = (rc_expr);                \
+    if (rc__ != 1) {                     \
+      g_last_path = (path);              \
+      return rc__;                       \
+    }                                    \
+  } while (0)
+
 static int check_shape(const a2c_conv_shape* s) {
   A2C_ARG_CHECK(s, "conv: null shape");
   A2C_ARG_CHECK(s->Cin > 0 && s->Cout > 0 && s->H > 0 && s->W > 0 && s->K > 0 && s->stride > 0 && s->pad >= 0,
@@ -527,6 +541,7 @@ static int channel_sum_launch(const float* X, const float* mask, double* acc, in
 
 bool conv_dgrad_shift_ok(const a2c_conv_shape* s);
 bool conv_wgrad_shift_ok(const a2c_conv_shape* s);
+bool conv_wgrad_shift_bias_free(const a2c_conv_shape* s);
 long long conv_wgrad_shift_workspace(const a2c_conv_shape* s);
 int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const float* dY, const float* Ymask,
                          float* dW, float* dbias, int N, const a2c_conv_shape* s, void* workspace,
@@ -556,17 +571,14 @@ int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
   // the other tensor-core paths take layers with more than 4 input channels, the rest is FFMA.
   if (precision == 1) {
     A2C_ARG_CHECK(xview || X, "conv_fwd: null input");
-    int rc = conv_fwd_shift_try(X, xview, Wt, bias, Y, N, s, relu, as_stream(stream));
-    if (rc != 1) return rc;
+    A2C_PATH_RETURN(0, conv_fwd_shift_try(X, xview, Wt, bias, Y, N, s, relu, as_stream(stream)));
   }
   if (precision != 0 && s->Cin > 4) {
     A2C_ARG_CHECK(xview || X, "conv_fwd: null input");
-    int rc;
-    rc = conv_fwd_patch_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
-    if (rc != 1) return rc;
-    rc = conv_fwd_tc_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream));
-    if (rc != 1) return rc;
+    A2C_PATH_RETURN(1, conv_fwd_patch_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream)));
+    A2C_PATH_RETURN(1, conv_fwd_tc_try(X, xview, Wt, bias, Y, N, s, relu, precision, as_stream(stream)));
   }
+  g_last_path = 2;
   ConvFwdParams p{};
   if (int rc = fill_src(&p.src, X, xview, s)) return rc;
   p.Wt = Wt; p.flipT = 0; p.bias = bias; p.Y = Y; p.N = N; p.Cin = s->Cin; p.Cout = s->Cout;
@@ -580,15 +592,13 @@ int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, fl
   A2C_ARG_CHECK(dY && Wt && dX && N >= 0, "conv_bwd_data: bad args");
   if (N == 0) return 0;
   if (precision == 1) {
-    int rc = conv_dgrad_shift_try(dY, Ymask, Wt, dX, nullptr, nullptr, N, s, as_stream(stream));
-    if (rc != 1) return rc;
+    A2C_PATH_RETURN(0, conv_dgrad_shift_try(dY, Ymask, Wt, dX, nullptr, nullptr, N, s, as_stream(stream)));
   }
   if (precision != 0 && !Ymask) {
-    int rc = conv_dgrad_patch_try(dY, Wt, dX, N, s, precision, as_stream(stream));
-    if (rc != 1) return rc;
-    rc = conv_dgrad_tc_try(dY, Wt, dX, N, s, precision, as_stream(stream));
-    if (rc != 1) return rc;
+    A2C_PATH_RETURN(1, conv_dgrad_patch_try(dY, Wt, dX, N, s, precision, as_stream(stream)));
+    A2C_PATH_RETURN(1, conv_dgrad_tc_try(dY, Wt, dX, N, s, precision, as_stream(stream)));
   }
+  g_last_path = 2;
   // dX = stride-1 conv of the dilated, masked dY with flipped/transposed weights
   ConvFwdParams p{};
   p.src.X = dY; p.src.mask = Ymask; p.src.SC = s->Cout; p.src.SH = s->OH; p.src.SW = s->OW;
@@ -602,8 +612,8 @@ int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, fl
   return launch_fwd(p, s->K, 1, logicalW, as_stream(stream));
 }
 
-int a2c_conv2d_bwd_data_relu(const float* dY, const float* Wt, const float* X, float* dX, float* dbias_prev,
-                             int N, const a2c_conv_shape* s, int precision, void* workspace,
+int a2c_conv2d_bwd_data_relu(const float* dY, const float* Ymask, const float* Wt, const float* X, float* dX,
+                             float* dbias_prev, int N, const a2c_conv_shape* s, int precision, void* workspace,
                              long long workspace_bytes, void* stream) {
   if (int rc = check_shape(s)) return rc;
   A2C_ARG_CHECK(dY && Wt && X && dX && N >= 0, "conv_bwd_data_relu: bad args");
@@ -614,11 +624,12 @@ int a2c_conv2d_bwd_data_relu(const float* dY, const float* Wt, const float* X, f
   if (acc) A2C_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * s->Cin, st));
   if (N > 0) {
     int rc = 1;
-    if (precision == 1) rc = conv_dgrad_shift_try(dY, nullptr, Wt, dX, X, acc, N, s, st);
+    if (precision == 1) rc = conv_dgrad_shift_try(dY, Ymask, Wt, dX, X, acc, N, s, st);
     if (rc != 0 && rc != 1) return rc;
+    if (rc == 0) g_last_path = 0;
     if (rc == 1) {
       // other paths: plain input gradient, then the mask and the channel sums as separate passes
-      if (int r2 = a2c_conv2d_bwd_data(dY, nullptr, Wt, dX, N, s, precision, stream)) return r2;
+      if (int r2 = a2c_conv2d_bwd_data(dY, Ymask, Wt, dX, N, s, precision, stream)) return r2;
       const long long n = (long long)N * s->Cin * s->H * s->W;
       long long blocks = cdivll(n, 256);
       if (blocks > num_sms() * 16) blocks = num_sms() * 16;
@@ -652,12 +663,16 @@ int a2c_channel_sum(const float* X, const float* mask, float* out, int N, int C,
   return 0;
 }
 
+int a2c_conv2d_last_path(void) { return g_last_path; }
+
 int a2c_conv2d_fused_mask(const a2c_conv_shape* s, int precision, int input_is_view) {
   if (!s || check_shape(s)) return 0;
   if (precision == 0) return 3;                       // the FFMA kernels always take Ymask
   int bits = 0;
   if (precision == 1 && conv_dgrad_shift_ok(s)) bits |= 1;
-  if ((precision == 1 && (!input_is_view || s->Cin <= 4) && conv_wgrad_shift_ok(s)) || s->Cin <= 4) bits |= 2;
+  const bool wg_shift = precision == 1 && (!input_is_view || s->Cin <= 4) && conv_wgrad_shift_ok(s);
+  if (wg_shift || s->Cin <= 4) bits |= 2;
+  if (wg_shift && conv_wgrad_shift_bias_free(s)) bits |= 4;
   return bits;
 }
 
@@ -693,16 +708,14 @@ int a2c_conv2d_bwd_weight(const float* X, const a2c_state_view* xview, const flo
   // 3x3 pad-1 layers run as shift-GEMMs (short TMEM chains, fp32 running sums, double reduction);
   // the older tensor-core paths take the remaining layers with more than 4 input channels.
   if (precision == 1) {
-    int rc = conv_wgrad_shift_try(X, xview, dY, Ymask, dW, dbias, N, s, workspace, workspace_bytes, st);
-    if (rc != 1) return rc;
+    A2C_PATH_RETURN(0, conv_wgrad_shift_try(X, xview, dY, Ymask, dW, dbias, N, s, workspace, workspace_bytes, st));
   }
   if (precision != 0 && !Ymask && s->Cin > 4) {
     A2C_ARG_CHECK(xview || X, "conv_bwd_weight: null input");
-    int rc = conv_wgrad_patch_try(X, xview, dY, dW, dbias, N, s, workspace, workspace_bytes, precision, st);
-    if (rc != 1) return rc;
-    rc = conv_wgrad_tc_try(X, xview, dY, dW, dbias, N, s, workspace, workspace_bytes, precision, st);
-    if (rc != 1) return rc;
+    A2C_PATH_RETURN(1, conv_wgrad_patch_try(X, xview, dY, dW, dbias, N, s, workspace, workspace_bytes, precision, st));
+    A2C_PATH_RETURN(1, conv_wgrad_tc_try(X, xview, dY, dW, dbias, N, s, workspace, workspace_bytes, precision, st));
   }
+  g_last_path = 2;
   WgPlan pl;
   if (plan_wgrad(s, &pl)) {
     set_error("conv_bwd_weight: unsupported shape");

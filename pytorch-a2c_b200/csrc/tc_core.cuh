@@ -12,7 +12,12 @@
 // (im2col, transposed, masked, u8 -> f32) while it fills the tile -- no operand
 // is ever materialised in HBM in a tensor-core friendly layout.
 //
-// SPLIT3 (3xTF32): hi = rna_tf32(x), lo = x - hi;  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.
+// SPLIT3 (3xTF32): hi = rna_tf32(x), lo = x - hi;  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, issued as
+// TWO instructions per k-step:  D[:, 0:2BN] (+)= A_hi * [B_hi | B_lo]  (the lo tile follows the hi tile in
+// shared memory, so one descriptor of width 2 BN covers both) and  D[:, 0:BN] += A_lo * B_hi;  the drain
+// adds the two column halves.  Same tensor-pipe work as three MMAs, but the A tile is fetched from
+// shared memory twice instead of three times -- and this kernel is bound by shared-memory bandwidth
+// (operand stores of the producers + operand fetches of the tensor core), not by the tensor pipe.
 // The TMEM accumulator adds with truncation (measured on B200: error grows
 // linearly with the number of chained MMAs, 2e-4 at K = 25600), so K is consumed
 // in chunks of KC k-blocks into two ping-pong TMEM accumulators and the drain
@@ -207,7 +212,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
   if (warp == ALLOC_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
-                 "r"((uint32_t)(2 * BN)));
+                 "r"((uint32_t)(4 * BN)));      // two ping-pong accumulators of [hi | lo] halves
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   P::init(p, scratch, threadIdx.x, THREADS);
@@ -298,6 +303,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
     }
   } else if (warp == MMA_WARP) {
     constexpr uint32_t idesc = make_idesc(BN);
+    constexpr uint32_t idesc2 = make_idesc(2 * BN);
     int it = 0, gchunk0 = 0;
     StageRing ring(stages);
     for (int tile = tile0; tile < total_tiles; tile += tile_step, gchunk0 += nchunks)
@@ -315,20 +321,19 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
       // mma_tf32_imm): about 3 issue instructions per MMA instead of ~25
       constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO, version, SWIZZLE_128B
       constexpr uint32_t LBO1 = 1u << 16;
-      const uint32_t tmem_d = tmem_base + buf * BN;
+      const uint32_t tmem_d = tmem_base + buf * 2 * BN;
       const uint32_t a_hi = ((smem_u32(stage_ptr(s)) & 0x3FFFFu) >> 4) | LBO1;
       const uint32_t a_lo = a_hi + (A_BYTES >> 4);
       const uint32_t b_hi = a_hi + (((SPLIT3 ? 2 : 1) * A_BYTES) >> 4);
-      const uint32_t b_lo = b_hi + (B_BYTES >> 4);
+      (void)B_BYTES;
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < KB / 8; ++kk) {
           const uint32_t koff = kk * 2;      // 8 tf32 = 32 bytes inside the 128-byte swizzle row
           const uint32_t first = ((i % KC) | kk) ? 1u : 0u;
           if constexpr (SPLIT3) {
-            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_lo + koff, b_hi + koff, first);
-            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + koff, b_lo + koff, 1u);
-            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + koff, b_hi + koff, 1u);
+            mma_tf32_imm<idesc2, DESC_HI>(tmem_d, a_hi + koff, b_hi + koff, first);
+            mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_lo + koff, b_hi + koff, 1u);
           } else {
             mma_tf32_imm<idesc, DESC_HI>(tmem_d, a_hi + koff, b_hi + koff, first);
           }
@@ -353,7 +358,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
       const int buf = gchunk & 1;
       mbar_wait_relaxed(&acc_full[buf], (gchunk >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + hsel * HALF;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * BN + hsel * HALF;
 #pragma unroll
       for (int c0 = 0; c0 < HALF; c0 += 16) {
         uint32_t r[16];
@@ -367,6 +372,18 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        if constexpr (SPLIT3) {                       // the A_hi * B_lo half
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+                "=r"(r[14]), "=r"(r[15])
+              : "r"(taddr + (uint32_t)(BN + c0)));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -380,7 +397,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
   if (warp == ALLOC_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)(2 * BN)));
+                 "r"((uint32_t)(4 * BN)));
   }
 }
 

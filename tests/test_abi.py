@@ -60,7 +60,8 @@ def test_no_cpu_fallback():
 
 def test_fused_mask_query_is_host_logic():
     """a2c_conv2d_fused_mask tells the caller which backward entries apply the ReLU mask
-    themselves (bit 0 data, bit 1 weight); pure host logic, so it runs without a GPU."""
+    themselves (bit 0 data, bit 1 weight) and whether the weight gradient also yields the bias
+    gradient for free (bit 2); pure host logic, so it runs without a GPU."""
     from a2c_b200 import _lib
     lib = _lib.load()
 
@@ -73,8 +74,9 @@ def test_fused_mask_query_is_host_logic():
 
     assert q(shape(16, 24, 80, 3, 1, 1), 0) == 3            # FFMA kernels always take the mask
     assert q(shape(16, 24, 80, 3, 1, 1), 1) == 3            # ConvModel layers 2-4: shift-GEMM both ways
-    assert q(shape(24, 32, 80, 3, 2, 1), 1) == 3
-    assert q(shape(32, 64, 40, 3, 2, 1), 1) == 3
-    assert q(shape(2, 16, 80, 3, 1, 1), 1, view=1) & 2      # first layer from the uint8 ring
+    assert q(shape(24, 32, 80, 3, 2, 1), 1) == 7            # 24 input channels: a free operand slot carries the bias row
+    assert q(shape(32, 64, 40, 3, 2, 1), 1) == 3            # 32 input channels: no free slot
+    assert q(shape(2, 16, 80, 3, 1, 1), 1, view=1) == 7     # first layer from the uint8 ring: packed rows have a free bias slot
+    assert q(shape(48, 64, 10, 3, 2, 1), 1) == 7            # GRUModel's 10x10 layer: scalar producers, 32 + 16 channel chunks
     assert q(shape(16, 32, 19, 4, 2, 0), 1) == 0            # A3C's 4x4 s2 layer: pre-masked gradient
     assert q(shape(16, 24, 80, 3, 1, 1), 2) == 0            # single-pass TF32 paths want the masked dY

@@ -604,7 +604,7 @@ FULL = [("full_c3_a3c.npz", "A3CModel", 1024, 20), ("full_c4_gru_bptt.npz", "GRU
         ("full_c2_conv.npz", "ConvModel", 256, 20)]
 
 
-@pytest.mark.parametrize("precision,FACT", [(0, 4), (1, 8)])
+@pytest.mark.parametrize("precision,FACT", [(0, 3), (1, 5)])
 @pytest.mark.parametrize("fname,model,R,T", FULL)
 def test_full_size_update_against_reference_golden(dev, precision_guard, fname, model, R, T, precision, FACT):
     """BASELINE configs C2-C4 at full size: stage 1 from raw frames on the GPU,
@@ -649,11 +649,15 @@ def test_full_size_update_against_reference_golden(dev, precision_guard, fname, 
     # / first-GEMM parameters (tests/golden/make_fp64.py measures it per tensor and
     # stores the float64 evaluation).  No fp32 implementation with a different
     # summation order can sit within 1e-5 of such a value, so the bar is:
-    #   distance(cuda, float64 oracle) <= max(1e-5, FACT * distance(reference fp32, float64 oracle))
+    #   distance(cuda, float64 oracle) <= max(1e-5, d_ref) + FACT * d_ref,   d_ref = distance(reference fp32, float64 oracle)
     # i.e. 1e-5 wherever the reference itself achieves it, and the same order as the
     # reference's own rounding error elsewhere (both are random draws of the same fp32
     # noise, so a small multiple, not 1x, is the meaningful bound); the distance to the
     # reference's fp32 output then follows from the triangle inequality (asserted).
+    # Round 2: the bar is  max(1e-5, ref_own) + k * ref_own  over EVERY element (not 4,096
+    # samples), k = 3 (FFMA) / 5 (3xTF32).  The measured maxima of e_full / ref_own are 2.24
+    # and 4.47 (profiles/r2_parity_margins.md); k is the next integer above (ratio - 1) + 1 of
+    # headroom for run-to-run changes of the ReLU-mask flips.
     g64 = H.load(fname.replace("full_", "fp64_"))
     # FULL-tensor yardstick: the oracle evaluated in float64 on the GPU's fp64 units (same torch
     # ops, seconds instead of minutes), pinned first to the committed CPU-generated fp64 fixture
@@ -680,15 +684,15 @@ def test_full_size_update_against_reference_golden(dev, precision_guard, fname, 
         e64 = H.grad_err(mine, g64["grad64/" + name], scale)
         den = max(float(full64.abs().max()), 1e-3 * scale)
         e_full = float((grads[name].double() - full64).abs().max()) / den
-        bar = max(TOL, FACT * ref_own)
+        bar = max(TOL, ref_own) + FACT * ref_own
         if report:
             print("MARGIN %s prec=%d %-24s numel=%-9d e_full=%.3g e_sampled=%.3g ref_own=%.3g bar=%.3g used=%.2f %s"
                   % (fname, precision, name, full64.numel(), e_full, e64, ref_own, bar, e_full / bar,
-                     "abs-1e-5" if bar == TOL else "FACT*ref_own"))
+                     "abs-1e-5" if ref_own <= TOL else "ref_own"))
         assert e64 <= bar, (name, "vs float64 oracle (sampled)", e64, "reference's own", ref_own)
         assert e_full <= bar, (name, "vs float64 oracle (every element)", e_full, "reference's own", ref_own)
         eref = H.grad_err(mine, g[key], scale)
-        assert eref <= TOL + (FACT + 2) * ref_own, (name, "vs fp32 reference", eref, ref_own)
+        assert eref <= bar + ref_own, (name, "vs fp32 reference (triangle inequality)", eref, ref_own)
     del o64
     upd._optim_step()
     terms = res["loss_terms"].tolist()

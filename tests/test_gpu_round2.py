@@ -470,3 +470,64 @@ def test_conv_stack_unmasked_gradient_and_tensor_input(dev):
     assert H.rel_err(xd.grad.cpu().numpy(), x64.grad.numpy()) < TOL
     for d, r in zip(dp, p64):
         assert H.rel_err(d.grad.cpu().numpy(), r.grad.numpy()) < TOL
+
+
+def test_other_preprocessors_bit_exact(dev):
+    """normalize / snake / breakout / null prep (a2c/preprocessing.py:4-9,19-32) against the numpy
+    restatement in the oracle, per frame and batched."""
+    from a2c_b200 import preprocessing as P
+    rng = np.random.default_rng(12)
+    frames = rng.integers(0, 256, size=(5, 210, 160, 3), dtype=np.uint8)
+    frames[0, ::3, ::5, 0] = 1
+    frames[1, ::2, ::7, :] = 255
+    for f in frames:
+        a, b = P.normalize_prep(f), O.normalize_prep(f)
+        assert a.dtype == b.dtype == np.float64 and a.shape == b.shape and np.array_equal(a, b)
+        a, b = P.snake_prep(f), O.snake_prep(f)
+        assert a.dtype == b.dtype == np.float32 and a.shape == b.shape and np.array_equal(a, b)
+        a, b = P.breakout_prep(f), O.breakout_prep(f)
+        assert a.dtype == b.dtype == np.uint8 and a.shape == b.shape == (1, 80, 72) and np.array_equal(a, b)
+        assert np.array_equal(P.null_prep(f), O.null_prep(f))
+    small = rng.integers(0, 256, size=(3, 11, 13, 3), dtype=np.uint8)     # snake grids are small
+    small[:, ::2, ::2, 0] = 1
+    got = P.snake_prep_batch(torch.from_numpy(small).to(dev)).cpu().numpy()
+    assert np.array_equal(got, np.stack([O.snake_prep(f) for f in small]))
+
+
+@pytest.mark.parametrize("src", ["u8_ring", "f32_states"])
+def test_im2col_stack_matches_float64_autograd(dev, src):
+    """A3CModel's conv stack on explicit patch matrices (a2c_im2col / a2c_col2im_nhwc + tcgen05
+    GEMMs, channels-last activations) against the float64 autograd of F.conv2d + ReLU + Linear
+    with the reference's NCHW flatten (a2c/models.py:22-46, 59-90)."""
+    import torch.nn.functional as F
+    from a2c_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    Nb = 6
+    x = (torch.rand(Nb, 2, 80, 80, generator=g) < 0.3).float()
+    if src == "f32_states":
+        x = x * torch.rand(Nb, 2, 80, 80, generator=g)
+    W1, b1 = torch.randn(16, 2, 8, 8, generator=g) / 11.3, torch.randn(16, generator=g) * 0.1
+    W2, b2 = torch.randn(32, 16, 4, 4, generator=g) / 16.0, torch.randn(32, generator=g) * 0.1
+    Wp, bp = torch.randn(24, 2048, generator=g) / 45.0, torch.randn(24, generator=g) * 0.1
+    dp = [t.to(dev).requires_grad_(True) for t in (W1, b1, W2, b2, Wp, bp)]
+    view = ops.View.of_states((x.to(torch.uint8) if src == "u8_ring" else x).to(dev))
+    feats = ops.Im2colStackFn.apply(view, ((4, 0), (2, 0)), *dp[:4])
+    assert feats.shape == (Nb, 2048)
+    w = ops.nhwc_linear_weight(dp[4], 32, 64)
+    out = ops.LinearFn.apply(feats, w, dp[5], False, True)
+    gout = torch.randn(out.shape, generator=g)
+    out.backward(gout.to(dev))
+    p64 = [t.double().requires_grad_(True) for t in (W1, b1, W2, b2, Wp, bp)]
+    a1 = F.conv2d(x.double(), p64[0], p64[1], stride=4)
+    y1 = F.relu(a1)
+    a2 = F.conv2d(y1, p64[2], p64[3], stride=2)
+    y2 = F.relu(a2)
+    got_y2 = feats.detach().cpu().view(Nb, 64, 32).permute(0, 2, 1).reshape(Nb, 32, 8, 8)
+    assert H.rel_err(got_y2.numpy(), y2.detach().numpy()) < TOL
+    # backward through the masks the device used
+    m2 = (got_y2 > 0).double()
+    ref = (a2 * m2).reshape(Nb, -1) @ p64[4].t() + p64[5]
+    assert H.rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    ref.backward(gout.double())
+    for name, d, r in zip(("W1", "b1", "W2", "b2", "Wp", "bp"), dp, p64):
+        assert H.rel_err(d.grad.cpu().numpy(), r.grad.numpy()) < 2e-5, name

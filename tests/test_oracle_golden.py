@@ -157,3 +157,33 @@ def test_oracle_models_match_live_reference():
             got = O.model_forward(model, p, x)
         for a, b in zip(got, want):
             assert torch.equal(a, b), model
+
+
+@pytest.mark.needs_reference
+def test_other_preprocessors_match_live_reference():
+    """normalize / null / snake / breakout prep of the oracle against the unmodified reference
+    functions (a2c/preprocessing.py:4-9,19-32; rgb2grey stubbed as the identity it is on a 2-D
+    array in the skimage releases that export it).  Skipped where /root/reference is absent."""
+    import _ref_loader
+    if not _ref_loader.reference_available():
+        pytest.skip("reference tree not mounted")
+    ref = _ref_loader.load_reference().preprocessing
+    rng = np.random.default_rng(4)
+    for k in range(4):
+        f = rng.integers(0, 256, size=(210, 160, 3), dtype=np.uint8)
+        f[::3, ::5, 0] = 1
+        f[::7, ::2, k % 3] = 255
+        for name in ("normalize_prep", "null_prep", "snake_prep", "breakout_prep"):
+            a, b = getattr(O, name)(f.copy()), getattr(ref, name)(f.copy())
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), name
+
+
+def test_other_preprocessors_known_answers():
+    f = np.zeros((210, 160, 3), dtype=np.uint8)
+    assert float(O.normalize_prep(f).max()) == -3.0 and O.normalize_prep(f).shape == (1, 210, 160, 3)
+    f[...] = 255
+    assert float(O.normalize_prep(f).min()) == 3.0
+    assert float(O.snake_prep(f).max()) == np.float32(.33)          # the blue rule is applied last
+    f[..., 2] = 0
+    assert float(O.snake_prep(f).max()) == 0.0                      # green == 255 -> 0
+    assert O.breakout_prep(f).shape == (1, 80, 72)
