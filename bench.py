@@ -97,14 +97,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, interval_ms=200):
+        self.index, self.rows, self.proc, self.interval_ms = index, [], None, interval_ms
 
     def start(self):
+        if self.interval_ms <= 0:
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", str(self.interval_ms)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -221,8 +223,10 @@ class Workload:
         return int(self.ingest.bytes_per_prefetch
                    + sum(v.numel() * v.element_size() for v in self.h_in.values()))
 
-    def step(self, from_host, prefetch_next=False):
-        """One pass of the hot path.  Returns the info dict (forces the D2H of the loss)."""
+    def step(self, from_host, prefetch_next=False, sync=True):
+        """One pass of the hot path.  sync=True returns the reference's info dict (one host
+        synchronisation: the D2H of the loss); sync=False only enqueues and returns the device
+        tensor of the five scalars."""
         ops, hyps, ring = self.ops, self.hyps, self.ring
         if self.steps_done > 0:
             ring.carry()
@@ -250,7 +254,9 @@ class Workload:
                            "gamma": hyps["gamma"], "lambda_": hyps["lambda_"]}}
         if self.h_states is not None:
             shared["h_states"] = self.h_states
-        return self.upd.update_model(shared)
+        if sync:
+            return self.upd.update_model(shared)
+        return self.upd.update_model_async(shared)     # device tensor [Loss, Pi, Val, Entropy, GradNorm]
 
     def barrier(self):
         if self.world > 1:
@@ -270,11 +276,26 @@ class Workload:
         info = None
         if from_host:
             self.ingest.prefetch(self.h_frames, self.h_reset)       # step 0's copy: inside the timed region
+        # The host only ENQUEUES inside the loop (the boxes of this pool show random 50-80 ms
+        # host stalls; with one synchronisation per step each of them idled the GPU).  Every step's
+        # five result scalars are still read back: a non-blocking D2H copy into pinned memory per
+        # step, consumed LAG steps later, so the queue stays at most LAG steps deep.
+        LAG = 3
+        if not hasattr(self, "_res_host"):
+            self._res_host = [torch.empty(5, dtype=torch.float32, pin_memory=True) for _ in range(LAG)]
+        res_ev = [torch.cuda.Event() for _ in range(LAG)]
         for i in range(steps):
-            info = self.step(from_host, prefetch_next=(i + 1 < steps))
+            if i >= LAG:
+                res_ev[i % LAG].synchronize()
+                info = self._res_host[i % LAG].tolist()
+            out5 = self.step(from_host, prefetch_next=(i + 1 < steps), sync=False)
+            self._res_host[i % LAG].copy_(out5, non_blocking=True)
+            res_ev[i % LAG].record()
             marks[i].record()
         e1.record()
         self.barrier()
+        info = dict(zip(("Loss", "Pi_Loss", "ValLoss", "Entropy", "GradNorm"),
+                        self._res_host[(steps - 1) % LAG].tolist()))
         ms = e0.elapsed_time(e1)
         self.last_step_ms = [round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks)]
         self.last_device_allocs = torch.cuda.memory_stats(self.dev).get("num_device_alloc", 0) - mallocs0
@@ -587,7 +608,7 @@ def run_ours(args):
     parity = dp_parity(world, rank, dev, dist, args.precision) if world > 1 else None
 
     wl = Workload(workload, world, rank, dev, args.precision, dist)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, args.clock_interval_ms)
     if rank == 0:
         sampler.start()
     rec = measure(wl, args.steps, args.warmup, pk, args.precision)
@@ -778,6 +799,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=int(os.environ.get("A2C_PRECISION", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-interval-ms", type=int, default=200,
+                    help="nvidia-smi sampling period during the timed region (the profiling recipe's 200 ms); 0 = off")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the c1/c3/c4/c5 records and the torch-eager GPU baseline of the N=1 line")
     args = ap.parse_args()

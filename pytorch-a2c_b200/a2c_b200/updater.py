@@ -275,13 +275,20 @@ class Updater:
                 "logits": logits_all[0] if len(logits_all) == 1 else torch.cat(logits_all),
                 "n_global": n_global, "chunks": len(bounds)}
 
+    def update_model_async(self, shared_data):
+        """update_model without the host synchronisation: enqueues the whole update and returns
+        a device tensor f32 [5] = (Loss, Pi_Loss, ValLoss, Entropy, GradNorm).  The caller reads it
+        when it needs the numbers (e.g. a non-blocking copy into pinned memory consumed a step
+        later), so the host can run ahead of the GPU and a host-side stall does not idle it."""
+        res = self.compute_gradients(shared_data)
+        self._optim_step()
+        return torch.cat([res["loss_terms"], self.flat.norm])
+
     def update_model(self, shared_data):
         """a2c/updater.py:33-137.  Returns {"Loss", "Pi_Loss", "ValLoss", "Entropy",
         "GradNorm"} (GradNorm a tensor, as in the reference)."""
         hyps = self.hyps
-        res = self.compute_gradients(shared_data)
-        self._optim_step()
-        terms = res["loss_terms"].tolist()           # one D2H sync per update
+        terms = self.update_model_async(shared_data).tolist()     # one D2H sync per update
         self.norm = self.flat.norm.clone()[0]
         self.info = {"Loss": terms[0], "Pi_Loss": terms[1], "ValLoss": terms[2],
                      "Entropy": terms[3], "GradNorm": self.norm}
