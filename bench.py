@@ -184,13 +184,16 @@ def pinned_copy(t):
 class Workload:
     """Resident state of one benchmark configuration on this rank."""
 
-    def __init__(self, name, world, rank, dev, precision, dist, data_parallel=True):
+    def __init__(self, name, world, rank, dev, precision, dist, data_parallel=True, graph=-1):
         from a2c_b200 import models, ops, updater
         self.ops, self.dist = ops, dist
         self.name, self.world, self.rank, self.dev = name, world, rank, dev
         model, _, T, fs, scaling, desc = WORKLOADS[name]
         R = slots_per_rank(name, world)
         self.model, self.R, self.T, self.fs, self.N = model, R, T, fs, R * T
+        # CUDA graph replay of stage 2 + update: a win for launch-bound small batches (C1: 1.8 -> 0.3 ms per
+        # update), a small loss for the big ones (C2: 42.7 -> 44.5 ms), so "auto" = small batches only
+        self.graph = (world == 1 and R * T <= 2048) if graph < 0 else bool(graph)
         self.hyps = dict(HYPS, n_tsteps=T, n_rollouts=R, n_envs=R, n_frame_stack=fs, model=model,
                          use_bptt=(model == "GRUModel"))
         ops.set_precision(precision)
@@ -246,6 +249,14 @@ class Workload:
             ring.push_frames(self.d_new_frames, self.d_new_reset, first_frame_index=1)
             self.rew_w.copy_(self.d_in["rewards"]); self.done_w.copy_(self.d_in["dones"])
             self.val_w.copy_(self.d_in["values"]); self.act_w.copy_(self.d_in["actions"])
+        if not sync or self.graph:
+            # stage 2 + update on the persistent rollout buffers; with graph on the Updater captures this
+            # call into a CUDA graph on its second use and replays it afterwards (one launch per update)
+            out5 = self.upd.update_from_rollout(ring.view(self.T), self.rew_w, self.done_w, self.val_w,
+                                                self.act_w, self.h_states, graph=self.graph)
+            if not sync:
+                return out5
+            return dict(zip(("Loss", "Pi_Loss", "ValLoss", "Entropy", "GradNorm"), out5.tolist()))
         deltas, advs, rets, stats = ops.delta_scan(self.rew_w, self.done_w, self.val_w, hyps["gamma"],
                                                    hyps["lambda_"])
         shared = {"states_view": ring.view(self.T), "states": None, "rewards": self.rew_w,
@@ -254,9 +265,7 @@ class Workload:
                            "gamma": hyps["gamma"], "lambda_": hyps["lambda_"]}}
         if self.h_states is not None:
             shared["h_states"] = self.h_states
-        if sync:
-            return self.upd.update_model(shared)
-        return self.upd.update_model_async(shared)     # device tensor [Loss, Pi, Val, Entropy, GradNorm]
+        return self.upd.update_model(shared)
 
     def barrier(self):
         if self.world > 1:
@@ -266,9 +275,11 @@ class Workload:
     def timed(self, from_host, steps, profile=False):
         from a2c_b200 import _lib
         self.barrier()
+        graph0 = self.graph
         if profile:
             _lib.PROFILE = {}
-        launches0 = _lib.launch_count()
+            self.graph = False                 # per-call events need the eager path
+        launches0 = _lib.launch_count() + self.upd.graph_replayed_kernels
         mallocs0 = torch.cuda.memory_stats(self.dev).get("num_device_alloc", 0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
@@ -301,11 +312,12 @@ class Workload:
         self.last_device_allocs = torch.cuda.memory_stats(self.dev).get("num_device_alloc", 0) - mallocs0
         prof = _lib.PROFILE
         _lib.PROFILE = None
+        self.graph = graph0
         if self.world > 1:
             t = torch.tensor([ms], device=self.dev)
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, _lib.launch_count() - launches0, info, prof
+        return ms, _lib.launch_count() + self.upd.graph_replayed_kernels - launches0, info, prof
 
     def settle(self, max_steps=30, window=3, tol=1.03):
         """Untimed steps BEFORE the W warm-up steps until `window` consecutive step times agree
@@ -420,6 +432,7 @@ def measure(wl, steps, warmup, pk, precision, profile_steps=3, with_stage1=True)
                                "buffer.  Rollout scalars are copied on the compute stream, before the DMA is "
                                "queued." % (wl.ingest.layout, wl.ingest.frame_bytes)},
            "gpu_launches": int(launches), "loss": info["Loss"], "host_enqueue_ms_per_step": host_ms,
+           "cuda_graph": bool(wl.graph),
            "step_ms": step_ms, "device_allocs_in_timed_region": dev_allocs, "settle_steps": settle,
            "update_micro_batches": wl.upd.last_chunks}
     roof, table, stages = roofline_from_profile(prof, min(steps, profile_steps), wl.R, wl.T, pk, stage1_ms,
@@ -540,6 +553,57 @@ def dp_parity(world, rank, dev, dist, precision):
     return out
 
 
+def acting_path(dev, precision, model="ConvModel", R=256, T=20, fs=2, reps=4):
+    """SURVEY section 8f-1, timed: Runner.rollout of the batched on-device acting step (per
+    timestep: one stage-1 launch for the R new frames, one batched inference forward, one fused
+    softmax / inverse-CDF sampler; then stage 2) against a recorded environment whose frames are
+    resident on the device.  The reference does this with R processes of batch-1 forwards."""
+    import queue
+
+    from a2c_b200 import models, ops, runner as runner_mod
+    ops.set_precision(precision)
+    hyps = dict(HYPS, n_tsteps=T, n_rollouts=R, n_envs=R, n_frame_stack=fs, model=model)
+    b = synth_batch(R, T, dev, 4321)
+    g = torch.Generator(device=dev).manual_seed(5)
+    traj_dev = {"frames": b["frames"], "reset": b["reset"], "rewards": b["rewards"].view(R, T),
+                "u": torch.rand((R, T), device=dev, generator=g)}
+
+    class _Env(runner_mod.RecordedVecEnv):
+        def __init__(self):                      # device tensors directly (no numpy round trip)
+            self.device, self.R, self.T = dev, R, T
+            self.frames, self.reset_flags = traj_dev["frames"], traj_dev["reset"]
+            self.rewards, self.u, self.t = traj_dev["rewards"], traj_dev["u"], 0
+
+        def rewind(self):
+            self.t = 0
+
+    torch.manual_seed(0)
+    net = models.get_model_class(model)([fs, 80, 80], 3, h_size=HYPS["h_size"]).to(dev)
+    datas = runner_mod.make_shared_data(R, T, fs, dev, h_size=HYPS["h_size"] if net.is_recurrent else None,
+                                        with_states=False)
+    q = queue.Queue(1)
+    q.put(-1.0)
+    rn = runner_mod.Runner(datas, hyps, None, None, q)
+    env = _Env()
+    rn.attach(net, env)
+    times = []
+    for i in range(reps + 1):
+        env.rewind()
+        torch.cuda.synchronize()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rn.rollout(net, 0, hyps)
+        e.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            times.append(a.elapsed_time(e))
+    ms = min(times)
+    return {"model": model, "n_envs": R, "n_tsteps": T, "ms_per_rollout": ms, "ms_per_timestep": ms / T,
+            "transitions_per_s": R * T / (ms / 1e3),
+            "what": "Runner.rollout: batched acting (stage 1 + inference forward + sampler per timestep, "
+                    "stage 2 at the end), frames resident on the device, best of %d rollouts" % reps}
+
+
 def gpu_eager_baseline(dev, N, steps=5, warmup=2):
     """Stage 3 + 4 + clip + RMSprop of C2 with stock torch.nn / autograd / torch.optim on the same
     B200 (fp32, allow_tf32 off: the library bar SURVEY.md section 2.1 names, and with TF32 on for
@@ -607,7 +671,7 @@ def run_ours(args):
     pk = peaks()
     parity = dp_parity(world, rank, dev, dist, args.precision) if world > 1 else None
 
-    wl = Workload(workload, world, rank, dev, args.precision, dist)
+    wl = Workload(workload, world, rank, dev, args.precision, dist, graph=args.graph)
     sampler = ClockSampler(local, args.clock_interval_ms)
     if rank == 0:
         sampler.start()
@@ -661,7 +725,7 @@ def run_ours(args):
         # one record per remaining BASELINE config (fewer steps: they are not the headline)
         extras = {}
         for name in ("c1", "c3", "c4", "c5"):
-            w2 = Workload(name, 1, 0, dev, args.precision, dist)
+            w2 = Workload(name, 1, 0, dev, args.precision, dist, graph=args.graph)
             r2 = measure(w2, max(3, min(args.steps, 5)), 3, pk, args.precision, profile_steps=2)
             r2["config"] = config_of(name, 1, args.precision)
             r2["steps"] = max(3, min(args.steps, 5))
@@ -673,6 +737,7 @@ def run_ours(args):
             torch.cuda.empty_cache()
         out["workloads"] = extras
         out["gpu_eager_baseline"] = gpu_eager_baseline(dev, 5120)
+        out["acting_path"] = acting_path(dev, args.precision)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(workload, budget_s=25.0)
     if rank == 0:
@@ -799,6 +864,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", type=int, default=int(os.environ.get("A2C_PRECISION", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", type=int, default=-1,
+                    help="replay stage 2 + the update as a CUDA graph (single GPU, one micro-batch, RMSprop): "
+                         "1 on, 0 off, -1 auto (batches of <= 2048 transitions)")
     ap.add_argument("--clock-interval-ms", type=int, default=200,
                     help="nvidia-smi sampling period during the timed region (the profiling recipe's 200 ms); 0 = off")
     ap.add_argument("--no-extras", action="store_true",

@@ -651,13 +651,14 @@ class Im2colStackFn(torch.autograd.Function):
             s = conv_shape(Cin, Cout, Hh, Ww, K, stride, pad)
             Kc = Cin * K * K
             M = N * s.OH * s.OW
-            col = torch.empty((M, Kc), dtype=torch.float32, device=dev)
             if l == 0:
                 assert view.fs == Cin
+                col = torch.empty((M, Kc), dtype=torch.float32, device=dev)
                 call("a2c_im2col", C.byref(view.c), None, ptr(col), N, C.byref(s), stream_ptr(),
                      tag="a2c_im2col|bytes|%d:%d,k%ds%d" % (N, Cin, K, stride), work=4.0 * M * Kc)
                 wf = W.reshape(Cout, Kc)                       # k = (ci, ky, kx): the reference's order
             else:
+                col = torch.empty((M, Kc), dtype=torch.float32, device=dev)
                 call("a2c_im2col", None, ptr(cur), ptr(col), N, C.byref(s), stream_ptr(),
                      tag="a2c_im2col|bytes|%d:%d,k%ds%d" % (N, Cin, K, stride), work=8.0 * M * Kc)
                 wf = W.permute(0, 2, 3, 1).reshape(Cout, Kc).contiguous()     # k = (ky, kx, ci)

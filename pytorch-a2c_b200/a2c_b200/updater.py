@@ -85,6 +85,9 @@ class Updater:
         self.ret_std = None
         self._step = 0
         self._count_cache = (None, None)
+        self._graphs = {}               # update_from_rollout(graph=True): buffers -> captured CUDA graph
+        self._chunk_cache = {}
+        self.graph_replayed_kernels = 0  # kernels of ours launched through graph replays (not seen by a2c_launch_count)
         self.last_chunks = 1            # micro-batches of the last update
         self.last_allreduce = None      # {"bytes", "buckets", "overlapped_bytes"} of the last update
 
@@ -124,11 +127,13 @@ class Updater:
         ~45 % of the free device memory by the model's activation estimate."""
         c = try_key(self.hyps, 'update_chunk_slots', None)
         if c is None:
-            est = getattr(self.net, 'activation_bytes_per_state', None)
-            per = est() if callable(est) else 4 << 20
-            free, _ = torch.cuda.mem_get_info(self.device)
-            free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
-            c = int(0.45 * free // (per * T))
+            c = self._chunk_cache.get((R, T))            # decided once per batch shape (no driver query per step)
+            if c is None:
+                est = getattr(self.net, 'activation_bytes_per_state', None)
+                per = est() if callable(est) else 4 << 20
+                free, _ = torch.cuda.mem_get_info(self.device)
+                free += torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+                c = self._chunk_cache[(R, T)] = int(0.45 * free // (per * T))
         return max(1, min(R, int(c)))
 
     @staticmethod
@@ -283,6 +288,66 @@ class Updater:
         res = self.compute_gradients(shared_data)
         self._optim_step()
         return torch.cat([res["loss_terms"], self.flat.norm])
+
+    # ---- rollout -> update in one call, optionally replayed as a CUDA graph -----------------------
+    def update_from_rollout(self, states_view, rewards, dones, values, actions, h_states=None, graph=None):
+        """Stage 2 + the whole update for a rollout whose buffers live at FIXED device addresses
+        (the Runner's / a trainer's persistent buffers): rewards / dones f32 [R*T] (raw; fixed up in
+        place as Runner.rollout leaves them, a2c/runner.py:228-245), values f32 [R, T+1], actions
+        i64 [R*T], states_view an ops.View of the plane ring.  Returns the device tensor of
+        update_model_async.
+
+        graph=True (default: hyps['cuda_graph'], off): the first call with a given set of buffers
+        runs eagerly (warm-up), the second is captured into a CUDA graph, later ones replay it -- one
+        launch instead of 60 .. 400, which is what a small (C1) or launch-heavy (GRU BPTT) update
+        needs on a busy host.  Restrictions: single process, one micro-batch, RMSprop (Adam's bias
+        correction is a per-step host scalar), hyper-parameters frozen at capture time."""
+        hyps = self.hyps
+        if graph is None:
+            graph = bool(try_key(hyps, 'cuda_graph', False))
+
+        def body():
+            deltas, advs, rets, stats = ops.delta_scan(rewards, dones, values, hyps['gamma'], hyps['lambda_'])
+            shared = {"states_view": states_view, "states": None, "rewards": rewards, "dones": dones,
+                      "deltas": deltas, "actions": actions,
+                      "scan": {"n": deltas.numel(), "advs": advs, "returns": rets, "stats": stats,
+                               "gamma": hyps['gamma'], "lambda_": hyps['lambda_']}}
+            if h_states is not None:
+                shared["h_states"] = h_states
+            return self.update_model_async(shared)
+
+        R_, T_ = states_view.R, states_view.T
+        ok = (graph and self._world() == 1 and isinstance(self.optim, optim.RMSprop)
+              and not try_key(hyps, 'norm_returns', False) and self._chunk_slots(R_, T_) >= R_)
+        if not ok:
+            return body()
+        key = (states_view.base.data_ptr(), states_view.R, states_view.T, states_view.fs,
+               rewards.data_ptr(), dones.data_ptr(), values.data_ptr(), actions.data_ptr(),
+               None if h_states is None else h_states.data_ptr())
+        ent = self._graphs.get(key)
+        if ent is None:                                  # first sight of these buffers: eager warm-up
+            self._graphs[key] = {"graph": None, "out": None, "keep": (states_view,)}
+            return body()
+        if ent["graph"] is None:                         # second call: capture (the capture also runs nothing,
+            step0 = self._step                           # so replay it once to execute this update)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = ops._lib.launch_count()
+            with torch.cuda.graph(g):
+                ent["out"] = body()
+            ent["kernels"] = ops._lib.launch_count() - n0      # kernels of liba2c_b200 recorded as graph nodes
+            ent["graph"] = g
+            self._step = step0                           # the capture pass advanced the host counters once:
+            for st in self.optim.state.values():         # undo, the replay below counts
+                if 'step' in st:
+                    st['step'] -= 1
+        ent["graph"].replay()
+        self.graph_replayed_kernels += ent["kernels"]
+        self._step += 1
+        for st in self.optim.state.values():
+            if 'step' in st:
+                st['step'] += 1
+        return ent["out"]
 
     def update_model(self, shared_data):
         """a2c/updater.py:33-137.  Returns {"Loss", "Pi_Loss", "ValLoss", "Entropy",

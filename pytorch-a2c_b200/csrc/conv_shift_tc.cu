@@ -143,7 +143,9 @@ __device__ __forceinline__ float4 rot4(float4 v, int r) {
 __device__ __forceinline__ void store_split(uint8_t* dst, int half_bytes, float a, float b, float c, float d) {
   const float4 h = make_float4(tf32_rna(a), tf32_rna(b), tf32_rna(c), tf32_rna(d));
   *reinterpret_cast<float4*>(dst) = h;
-  *reinterpret_cast<float4*>(dst + half_bytes) = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);
+  // (lo rounded to TF32 as well: see tc_core.cuh store_chunk)
+  *reinterpret_cast<float4*>(dst + half_bytes) =
+      make_float4(tf32_rna(a - h.x), tf32_rna(b - h.y), tf32_rna(c - h.z), tf32_rna(d - h.w));
 }
 
 // FIRST: first-layer variant (<= 4 real channels padded to one k-step, optional uint8 ring source,

@@ -103,7 +103,8 @@ __device__ __forceinline__ float4 rot4(float4 v, int r) {
 __device__ __forceinline__ void wg_store_split(uint8_t* dst, int half_bytes, float a, float b, float c, float d) {
   const float4 h = make_float4(tf32_rna(a), tf32_rna(b), tf32_rna(c), tf32_rna(d));
   *reinterpret_cast<float4*>(dst) = h;
-  *reinterpret_cast<float4*>(dst + half_bytes) = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);
+  *reinterpret_cast<float4*>(dst + half_bytes) =
+      make_float4(tf32_rna(a - h.x), tf32_rna(b - h.y), tf32_rna(c - h.z), tf32_rna(d - h.w));
 }
 
 // Stores the hi / lo split of 4 channels (16-byte chunk `cg` of a dY position row).  Unpacked: the lo copy
@@ -116,7 +117,7 @@ __device__ __forceinline__ void wg_store_dy(uint8_t* buf, uint32_t pos, uint32_t
   uint8_t* lo = opack ? row + ((((c32 + 2u) ^ (pos & 3u)) << 5) | c16) : hi + o_half;
   const float4 h = make_float4(tf32_rna(a), tf32_rna(b), tf32_rna(c), tf32_rna(d));
   *reinterpret_cast<float4*>(hi) = h;
-  *reinterpret_cast<float4*>(lo) = make_float4(a - h.x, b - h.y, c - h.z, d - h.w);
+  *reinterpret_cast<float4*>(lo) = make_float4(tf32_rna(a - h.x), tf32_rna(b - h.y), tf32_rna(c - h.z), tf32_rna(d - h.w));
 }
 
 __device__ __forceinline__ void wg_tmem_ld16(uint32_t taddr, uint32_t* r) {
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
             const uint32_t pos = (uint32_t)(p.ncx * r * p.PWx + (p.S == 1 ? xp : (xp & 1) * p.PWx + (xp >> 1)));
             const uint32_t c16 = ((uint32_t)cg & 1u) << 4, c32 = (uint32_t)cg >> 1;
             const float4 h = make_float4(tf32_rna(c4[0]), tf32_rna(c4[1]), tf32_rna(c4[2]), tf32_rna(c4[3]));
-            const float4 l = make_float4(c4[0] - h.x, c4[1] - h.y, c4[2] - h.z, c4[3] - h.w);
+            const float4 l = make_float4(tf32_rna(c4[0] - h.x), tf32_rna(c4[1] - h.y), tf32_rna(c4[2] - h.z), tf32_rna(c4[3] - h.w));
             uint8_t* d = buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16);
             *reinterpret_cast<float4*>(d) = h;
             *reinterpret_cast<float4*>(d + p.x_half) = l;
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
             if (xp < 0 || xp >= XN) continue;
             const uint32_t pos = (uint32_t)(rowpos + (p.S == 1 ? xp : (xp & 1) * p.PWx + (xp >> 1)));
             const float4 h = make_float4(tf32_rna(px[j][0]), tf32_rna(px[j][1]), tf32_rna(px[j][2]), tf32_rna(px[j][3]));
-            const float4 l = make_float4(px[j][0] - h.x, px[j][1] - h.y, px[j][2] - h.z, px[j][3] - h.w);
+            const float4 l = make_float4(tf32_rna(px[j][0] - h.x), tf32_rna(px[j][1] - h.y), tf32_rna(px[j][2] - h.z), tf32_rna(px[j][3] - h.w));
             // buffers are 1024-byte aligned: the swizzle phase of a row is its position & 3
             uint8_t* d = buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16);
             *reinterpret_cast<float4*>(d) = h;

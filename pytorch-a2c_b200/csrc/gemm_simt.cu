@@ -240,8 +240,9 @@ splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, l
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const int m = (int)(e / N), n = (int)(e - (long long)m * N);
-    float s = 0.0f;
-    for (int z = 0; z < splits; ++z) s += partial[(long long)z * total + e];
+    double sd = 0.0;                                   // partial products of a long reduction: sum in double
+    for (int z = 0; z < splits; ++z) sd += (double)partial[(long long)z * total + e];
+    float s = (float)sd;
     if (bias) s += bias[n];
     float* dst = C + (long long)m * ldc + n;
     if (beta) s += *dst;

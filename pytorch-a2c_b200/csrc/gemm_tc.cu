@@ -23,6 +23,10 @@ struct GemmOperand {
   int mode;   // 0: k contiguous, 1: mn contiguous
 };
 
+__device__ __forceinline__ float4 gemm_ld4(const GemmOperand& op, long long off) {
+  return __ldg(reinterpret_cast<const float4*>(op.p + off));
+}
+
 struct GemmParams {
   GemmOperand A, B;
   float* C;
@@ -62,8 +66,7 @@ __device__ __forceinline__ void gemm_load(const GemmOperand& op, int MN, int K, 
       const int u = i * PROD_THREADS + t, row = u >> 3, chunk = u & 7;
       const int mn = mn0 + row, k = k0 + chunk * 4;
       f.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < ROWS && mn < MN && k < K)
-        f.v[i] = __ldg(reinterpret_cast<const float4*>(op.p + (long long)mn * op.s_mn + k));
+      if (row < ROWS && mn < MN && k < K) f.v[i] = gemm_ld4(op, (long long)mn * op.s_mn + k);
     }
   } else {
     // mn contiguous: unit = (group of 4 rows, k-chunk): 4 loads along mn (transposed at store time).
@@ -74,8 +77,7 @@ __device__ __forceinline__ void gemm_load(const GemmOperand& op, int MN, int K, 
     for (int j = 0; j < 4; ++j) {
       const int k = k0 + chunk * 4 + j;
       f.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g * 4 < ROWS && mn < MN && k < K)
-        f.v[j] = __ldg(reinterpret_cast<const float4*>(op.p + (long long)k * op.s_k + mn));
+      if (g * 4 < ROWS && mn < MN && k < K) f.v[j] = gemm_ld4(op, (long long)k * op.s_k + mn);
     }
   }
 }
@@ -102,11 +104,15 @@ __device__ __forceinline__ void gemm_store(const GemmOperand& op, const GemmFrag
   }
 }
 
-template <int BN, bool SPLIT3>
+// KCHAIN: k-blocks chained in one TMEM accumulator before the drain adds the partial result in fp32
+// registers (round to nearest); TMEM adds truncate.  (Chains of 2 were tried for the weight-gradient
+// GEMMs over millions of rows: 2x slower -- the drain becomes the bottleneck -- and no more accurate;
+// the residual error of those gradients comes from flipped ReLU mask bits, not from accumulation.)
+template <int BN, bool SPLIT3, int KCHAIN = 8>
 struct GemmProblem {
   using Params = GemmParams;
   // 16 producer warps, loads two k-blocks ahead: 64 KB of operand loads in flight per SM
-  static constexpr int NA = 8, NB = 8, KC = 8, DEPTH = 2;
+  static constexpr int NA = 8, NB = 8, KC = KCHAIN, DEPTH = 2;
   struct AState {};
   using AFrag = GemmFrag<TM>;
   using BFrag = GemmFrag<BN>;

@@ -91,7 +91,8 @@ im2col_planar_kernel(const Im2colParams p) {
 // rows are written with coalesced 128-bit stores and no per-element index arithmetic beyond one
 // small division.  Used when W % 4 == 0, S % 4 == 0, P % 4 == 0 and the tile fits 48 KB; the
 // generic kernel above covers everything else.  (Measured, first A3C layer at C3, 3.8 GB of patch
-// matrix: generic 2.6 ms, this one see DESIGN.md.)
+// matrix: generic 2.6 ms, this one 2.1 ms.  A uint8 patch matrix -- 4x fewer bytes -- was tried and
+// dropped: neither this kernel nor the GEMM that consumes it is bandwidth-bound.)
 __global__ void __launch_bounds__(256)
 im2col_planar_rows_kernel(const Im2colParams p) {
   extern __shared__ float tile[];                    // [C][K][W]
@@ -128,15 +129,15 @@ im2col_planar_rows_kernel(const Im2colParams p) {
       reinterpret_cast<float4*>(tile)[u] = o;
     }
     __syncthreads();
-    float* out = p.col + ((n * p.OH + oy) * (long long)p.OW) * Kc;
-    const int per_row = Kc >> 2;                     // float4 per patch row
+    const long long out_off = ((n * p.OH + oy) * (long long)p.OW) * Kc;
+    const int per_row = Kc >> 2;                     // 4-element groups per patch row
     for (int u = threadIdx.x; u < p.OW * per_row; u += blockDim.x) {
       const int ox = u / per_row, q = u - ox * per_row;
       const int kx0 = (q % K4) << 2, ck = q / K4;    // ck = ci*K + ky
       const int x0 = ox * p.S + kx0 - p.P;           // multiple of 4
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       if ((unsigned)x0 < (unsigned)p.W) o = reinterpret_cast<const float4*>(tile)[ck * W4 + (x0 >> 2)];
-      reinterpret_cast<float4*>(out)[u] = o;
+      reinterpret_cast<float4*>(p.col + out_off)[u] = o;
     }
   }
 }

@@ -531,3 +531,48 @@ def test_im2col_stack_matches_float64_autograd(dev, src):
     ref.backward(gout.double())
     for name, d, r in zip(("W1", "b1", "W2", "b2", "Wp", "bp"), dp, p64):
         assert H.rel_err(d.grad.cpu().numpy(), r.grad.numpy()) < 2e-5, name
+
+
+@pytest.mark.parametrize("model,bptt", [("FCModel", False), ("ConvModel", False), ("GRUModel", True)])
+def test_update_from_rollout_cuda_graph_equals_eager(dev, model, bptt):
+    """Stage 2 + the whole update replayed as a CUDA graph (Updater.update_from_rollout(graph=True))
+    gives the same parameters and loss terms as the eager path, update after update."""
+    from a2c_b200 import ops, updater
+    R, T, fs, h = 6, 5, 2, 32
+    hyps = dict(HY, n_tsteps=T, n_rollouts=R, use_bptt=bptt)
+    trajs = [synth.make_trajectory(R, T, seed=70 + k, first_rollout=(k == 0)) for k in range(4)]
+    results = {}
+    for graph in (False, True):
+        net = build_net(model, fs, h, dev)
+        upd = updater.Updater(net, hyps)
+        ring = ops.PlaneRing(R, T, fs, dev)
+        rew = torch.empty(R * T, device=dev)
+        dn = torch.empty(R * T, device=dev)
+        val = torch.empty((R, T + 1), device=dev)
+        act = torch.empty(R * T, dtype=torch.int64, device=dev)
+        hst = torch.from_numpy(synth.hashed_tensor((R * T, h), 999, 0.5)).float().to(dev) if model == "GRUModel" else None
+        outs = []
+        for k, tr in enumerate(trajs):
+            fr = torch.from_numpy(tr["frames"]).to(dev)
+            rs = torch.from_numpy(tr["reset"]).to(dev)
+            if k == 0:
+                ring.push_frames(fr, rs)
+            else:
+                ring.carry()
+                ring.push_frames(fr[:, 1:].contiguous(), rs[:, 1:].contiguous(), first_frame_index=1)
+            done = ((tr["reset"][:, 1:] != 0) | (tr["rewards"] != 0)).astype(np.float32)
+            rew.copy_(torch.from_numpy(tr["rewards"].reshape(-1).copy()))
+            dn.copy_(torch.from_numpy(done.reshape(-1).copy()))
+            val.copy_(torch.from_numpy(tr["values"]))
+            act.copy_(torch.from_numpy(np.random.default_rng(k).integers(0, 3, size=R * T)))
+            out = upd.update_from_rollout(ring.view(T), rew, dn, val, act, hst, graph=graph)
+            outs.append(out.clone().cpu())
+        if graph:
+            assert any(e["graph"] is not None for e in upd._graphs.values()), "no graph was captured"
+            assert upd._step == len(trajs)
+        results[graph] = (outs, [p.detach().clone() for p in net.parameters()])
+    for a, b in zip(results[False][0], results[True][0]):
+        assert torch.allclose(a, b, rtol=2e-5, atol=1e-7), (a, b)
+    step = hyps["lr"] / 0.1
+    for pa, pb in zip(results[False][1], results[True][1]):
+        assert float((pa - pb).abs().max()) <= 1e-6 * float(pa.abs().max()) + 0.02 * step
