@@ -9,9 +9,10 @@
 // A k-step is 8 consecutive positions (= 8 rows, 1 KB); channel slots are the M / N extent.  A
 // tap is a shift of the X start address by whole rows, so there is no im2col and no transpose.
 //
-//   stride 1, Cin <= 16 : every X row also carries the channels of the image row below it in
-//                         slots [16, 32), so one 32-slot atom covers ky = 0, 1 and a second atom
-//                         two image rows further down covers ky = 2: M = 64, one MMA per kx.
+//   Cin <= 16           : an X row holds [hi (16 slots) | lo (16 slots)] of its channels in ONE 32-slot atom, so
+//                         the atoms of rows ky = 0, 1, 2 stack along M (M = 128, full tensor rate) and a single MMA
+//                         per kx against [dY_hi | dY_lo] yields all hi / lo cross products: no second MMA, no
+//                         separate lo copy of the band (half the X footprint -> taller bands).
 //   stride 1, Cin <= 4  : (first layers) rows y, y+1, y+2 share one atom, 4 slots each: M = 64.
 //                         The input may be the uint8 plane ring (state view): {0,1} values are
 //                         exact in TF32, so the x_lo * dy_hi product is skipped.
@@ -69,7 +70,7 @@ struct WgShiftParams {
   int scalar_w;          // W or OW not a multiple of 4 (10x10 / 5x5 planes): one pixel per lane, scalar loads
   int opack;             // Cout <= 16: a dY row holds [hi (16 slots) | lo (16 slots)] in ONE 32-slot atom, no second copy
   int S;                 // stride
-  int pack2;             // stride 1, Cin <= 16: slots [16,32) = channels of the next image row
+  int xpack;             // Cin <= 16 (not a first layer): X rows hold [hi 16 | lo 16] in one atom, no lo copy
   int ncx;               // x-parity planes per X row (1, or 2 for stride 2)
   int OWc, ncol;         // output columns per chunk, chunks per row
   int PWx, PWo;          // positions per X plane row / per dY row (PWo multiple of 8)
@@ -351,13 +352,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
             const float4 l = make_float4(tf32_rna(c4[0] - h.x), tf32_rna(c4[1] - h.y), tf32_rna(c4[2] - h.z), tf32_rna(c4[3] - h.w));
             uint8_t* d = buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16);
             *reinterpret_cast<float4*>(d) = h;
-            *reinterpret_cast<float4*>(d + p.x_half) = l;
-            if (p.pack2 && r > 0) {
-              const uint32_t pos2 = pos - (uint32_t)p.PWx;
-              uint8_t* d2 = buf + pos2 * WG_ROWB + ((((c32 + 2u) ^ (pos2 & 3u)) << 5) | c16);
-              *reinterpret_cast<float4*>(d2) = h;
-              *reinterpret_cast<float4*>(d2 + p.x_half) = l;
-            }
+            *reinterpret_cast<float4*>(p.xpack ? buf + pos * WG_ROWB + ((((c32 + 2u) ^ (pos & 3u)) << 5) | c16)
+                                               : d + p.x_half) = l;
           }
         } else {
         const float4* simg = reinterpret_cast<const float4*>(ximg);
@@ -390,13 +386,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
             // buffers are 1024-byte aligned: the swizzle phase of a row is its position & 3
             uint8_t* d = buf + pos * WG_ROWB + (((c32 ^ (pos & 3u)) << 5) | c16);
             *reinterpret_cast<float4*>(d) = h;
-            *reinterpret_cast<float4*>(d + p.x_half) = l;
-            if (p.pack2 && r > 0) {                                    // also the "row below" of the previous band row
-              const uint32_t pos2 = pos - (uint32_t)p.PWx;
-              uint8_t* d2 = buf + pos2 * WG_ROWB + ((((c32 + 2u) ^ (pos2 & 3u)) << 5) | c16);
-              *reinterpret_cast<float4*>(d2) = h;
-              *reinterpret_cast<float4*>(d2 + p.x_half) = l;
-            }
+            // (packed: the lo part is chunk cg + 4 of the same row, i.e. slots [16, 32))
+            *reinterpret_cast<float4*>(p.xpack ? buf + pos * WG_ROWB + ((((c32 + 2u) ^ (pos & 3u)) << 5) | c16)
+                                               : d + p.x_half) = l;
           }
         }
         }
@@ -510,7 +502,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
                   //  not aligned to the 512-byte pattern needs NO base offset in the descriptor)
                   mma_tf32_imm<ID2, WG_DESC_HI>(tmem_d + kx * 2 * NH, a_hi, b_row, acc);
                   // ({0,1} ring sources are exact in TF32: no X_lo term)
-                  if (p.nsplit == 2) mma_tf32_imm<ID1, WG_DESC_HI>(tmem_d + kx * 2 * NH, a_hi + xhalf16, b_row, 1u);
+                  // (packed X rows carry their lo part as extra M rows of the same atom: nothing more to issue)
+                  if (p.nsplit == 2 && !p.xpack) mma_tf32_imm<ID1, WG_DESC_HI>(tmem_d + kx * 2 * NH, a_hi + xhalf16, b_row, 1u);
                 }
                 acc = 1u;
                 a_row += 8 * 8;
@@ -579,7 +572,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
 }
 
 // dW from the per-CTA partials (double accumulation).  Accumulator row of (ky, ci):
-//   first layer (Cin <= 4) : ky * 4 + ci     packed (stride 1, Cin <= 16) : ky * 16 + ci     otherwise : ky * 32 + ci
+//   first layer (Cin <= 4) : ky * 4 + ci     otherwise : ky * 32 + ci  (packed X, Cin <= 16: plus row + 16 for the lo part)
 // M = 64 accumulators live in TMEM lanes (m % 16) + 32 * (m / 16).
 __global__ void __launch_bounds__(256)
 wg_shift_reduce_kernel(const float* __restrict__ partial, int grid, int pack, int mrows, int Cin, int CinTot,
@@ -594,11 +587,14 @@ wg_shift_reduce_kernel(const float* __restrict__ partial, int grid, int pack, in
     const int ky = r % 3;
     r /= 3;
     const int ci = r % Cin, co = is_bias ? e - nw : r / Cin;
-    const int m = is_bias ? bias_row : (pack == 3 ? ky * 4 + ci : (pack == 2 ? ky * 16 + ci : ky * 32 + ci));
+    const int m = is_bias ? bias_row : (pack == 3 ? ky * 4 + ci : ky * 32 + ci);
     const int lane_row = mrows == 128 ? m : (m & 15) + 32 * (m >> 4);
     double s = 0.0;
     for (int b = 0; b < grid; ++b)
       s += (double)partial[((size_t)b * 128 + lane_row) * WG_NACC + kx * WG_N + co];
+    if (pack == 4 && !is_bias)                 // packed X: the lo channels' products sit 16 accumulator rows further
+      for (int b = 0; b < grid; ++b)
+        s += (double)partial[((size_t)b * 128 + lane_row + 16) * WG_NACC + kx * WG_N + co];
     if (is_bias) dbias[n0 + co] = (float)s;
     else dW[(((size_t)(n0 + co) * CinTot + ci0 + ci) * 3 + ky) * 3 + kx] = (float)s;
   }
@@ -666,7 +662,7 @@ static bool wg_plan(WgShiftParams* p) {
     const long long xh = ((long long)p->xrows * p->ncx * p->PWx * WG_ROWB + 1023) & ~1023LL;
     const long long oh = ((long long)p->Rb * p->PWo * WG_ROWB + 1023) & ~1023LL;
     // (sources that are exact in TF32 have no lo copy; packed dY rows hold hi and lo side by side)
-    p->x_half = (int)xh; p->x_buf = (int)((p->nsplit == 2 ? 2 : 1) * xh);
+    p->x_half = (int)xh; p->x_buf = (int)(((p->nsplit == 2 && !p->xpack) ? 2 : 1) * xh);
     p->o_half = (int)oh; p->o_buf = (int)((p->opack ? 1 : 2) * oh);
     if (wg_smem_bytes(*p) <= (size_t)WG_SMEM_LIMIT) return true;
   }
@@ -717,7 +713,7 @@ bool conv_wgrad_shift_bias_free(const a2c_conv_shape* s) {
   if (!conv_wgrad_shift_ok(s)) return false;
   const bool first = s->Cin <= 4 && s->stride == 1;
   if (first) return true;
-  if (s->stride == 1 && s->Cin <= 16) return false;            // pack2: both 16-slot halves carry channels
+  if (s->Cin <= 16) return false;                              // packed X rows: slots [16, 32) carry the lo parts
   for (int ci0 = 0; ci0 < s->Cin; ci0 += 32)
     if ((s->Cin - ci0 < 32 ? s->Cin - ci0 : 32) <= 28) return true;
   return false;
@@ -762,9 +758,9 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   p.ncol = s->OW / owc;
   p.PWx = S == 1 ? p.OWc + 2 : p.OWc + 1;
   p.PWo = (p.OWc + 7) & ~7;
-  p.pack2 = (S == 1 && s->Cin <= 16 && !first) ? 1 : 0;
-  p.mrows = (p.pack2 || p.pack3) ? 64 : 128;
-  p.a_lbo = (p.pack2 ? 2 : 1) * p.ncx * p.PWx * tc::WG_ROWB;     // one (packed: two) source rows
+  p.xpack = (s->Cin <= 16 && !first) ? 1 : 0;
+  p.mrows = p.pack3 ? 64 : 128;
+  p.a_lbo = p.ncx * p.PWx * tc::WG_ROWB;                         // one source row between the ky atoms
   if (p.a_lbo >= (1 << 18)) return 1;
   if (!tc::wg_plan(&p)) return 1;
   // rows per accumulator chunk: a TMEM chain of at most ~64 MMAs (2-3 per k-step)
@@ -788,7 +784,7 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
   }
   // bias gradient from the MMA when the X rows have a free 4-slot chunk (first layers: chunk 3 of the
   // packed atom; chunks of 20..28 channels: chunk cin / 4); otherwise the separate masked sum below
-  p.ones_chunk = bias_done ? -1 : (first ? 3 : ((!p.pack2 && cin <= 28) ? cin / 4 : -1));
+  p.ones_chunk = bias_done ? -1 : (first ? 3 : ((!p.xpack && cin <= 28) ? cin / 4 : -1));
   const int bias_row = p.ones_chunk >= 0 ? 4 * p.ones_chunk : -1;     // accumulator row (ky = 0 atom)
   p.partial = reinterpret_cast<float*>(bias_acc + ((s->Cout + 1) & ~1));
   p.dbg = debug_knob("A2C_WG_DBG");
@@ -806,7 +802,7 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
     A2C_LAUNCH_CHECK();
     const int nco = s->Cout - n0 < tc::WG_N ? s->Cout - n0 : tc::WG_N;
     tc::wg_shift_reduce_kernel<<<cdiv(nco * cin * 9 + nco, 256), 256, 0, st>>>(
-        p.partial, grid, p.pack3 ? 3 : (p.pack2 ? 2 : 0), p.mrows, cin, s->Cin, ci0, s->Cout, n0, dW, bias_row,
+        p.partial, grid, p.pack3 ? 3 : (p.xpack ? 4 : 0), p.mrows, cin, s->Cin, ci0, s->Cout, n0, dW, bias_row,
         bias_row >= 0 ? dbias : nullptr);
     g_launches++;
     A2C_LAUNCH_CHECK();
