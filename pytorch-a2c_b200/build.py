@@ -16,7 +16,7 @@ LIB = os.path.join(OUT_DIR, "liba2c_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math" if False else "-DNDEBUG"]
+         "-Xcompiler", "-fPIC", "-DNDEBUG"] + os.environ.get("A2C_NVCC_FLAGS", "").split()
 
 
 def _sources():

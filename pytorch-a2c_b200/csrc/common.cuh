@@ -136,10 +136,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 // For waits that are expected to be long (a role that is ahead of the pipeline): back off
-// so the spinning warp does not take issue slots from the warps doing the work.
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+// so the spinning warp does not take issue slots from the warps doing the work.  The wait is
+// given a suspend-time hint (the hardware parks the warp until the phase completes or the hint
+// expires) and sleeps between polls.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns = 64) {
   if (mbar_try_wait(bar, parity)) return;
-  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+  while (!mbar_try_wait_hint(bar, parity, ns)) __nanosleep(ns);
 }
 
 // Stage index + phase parity of a circular mbarrier pipeline, advanced without div/mod.

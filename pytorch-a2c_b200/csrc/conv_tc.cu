@@ -140,26 +140,28 @@ struct ConvFwdProblem {
   }
   using AFrag = Frag<16>;
   using BFrag = Frag<BN / 4>;
+  struct BState {};
+  static __device__ __forceinline__ void b_setup(const Params&, const uint8_t*, int, int, BState&) {}
   static __device__ __forceinline__ void load_a(const Params& p, const AState& st, const uint8_t* scratch,
                                                 int, int kb, int t, AFrag& f) {
     const uint32_t* tab = reinterpret_cast<const uint32_t*>(scratch) + kb * KB + (t >> 7) * 16;
 #pragma unroll
     for (int j = 0; j < 16; ++j) f.v[j] = xrow_load(p, st, tab[j]);
   }
-  static __device__ __forceinline__ void store_a(const Params&, const AFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+  static __device__ __forceinline__ void store_a(const Params&, const AState&, const AFrag& f, uint8_t* hi, uint8_t* lo, int t) {
     const int row = t & 127, c0 = (t >> 7) * 4;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
       store_chunk<SPLIT3>(hi, lo, row, c0 + c,
                           make_float4(f.v[c * 4], f.v[c * 4 + 1], f.v[c * 4 + 2], f.v[c * 4 + 3]));
   }
-  static __device__ __forceinline__ void load_b(const Params& p, const uint8_t*, int n0, int kb, int t, BFrag& f) {
+  static __device__ __forceinline__ void load_b(const Params& p, const BState&, const uint8_t*, int n0, int kb, int t, BFrag& f) {
     load_weights<BN, 32 * NB>(f, t, [&](int row, int kk) {
       const int co = n0 + row, k = kb * KB + kk;
       return (co < p.Cout && k < p.red) ? __ldg(p.wt + (long long)co * p.red + k) : 0.0f;
     });
   }
-  static __device__ __forceinline__ void store_b(const Params&, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+  static __device__ __forceinline__ void store_b(const Params&, const BState&, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
     store_weights<BN, SPLIT3, 32 * NB>(f, hi, lo, t);
   }
   template <int HALF>
@@ -214,6 +216,8 @@ struct ConvDgradProblem {
   }
   using AFrag = Frag<16>;
   using BFrag = Frag<BN / 4>;
+  struct BState {};
+  static __device__ __forceinline__ void b_setup(const Params&, const uint8_t*, int, int, BState&) {}
   static __device__ __forceinline__ void load_a(const Params& p, const AState& st, const uint8_t* scratch,
                                                 int, int kb, int t, AFrag& f) {
     const uint32_t* tab = reinterpret_cast<const uint32_t*>(scratch) + kb * KB + (t >> 7) * 16;
@@ -229,14 +233,14 @@ struct ConvDgradProblem {
       v[j] = ok ? __ldg(st.ptr + (int)(e & 0xFFFFF) + oy * p.OW + ox) : 0.0f;
     }
   }
-  static __device__ __forceinline__ void store_a(const Params&, const AFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+  static __device__ __forceinline__ void store_a(const Params&, const AState&, const AFrag& f, uint8_t* hi, uint8_t* lo, int t) {
     const int row = t & 127, c0 = (t >> 7) * 4;
 #pragma unroll
     for (int c = 0; c < 4; ++c)
       store_chunk<SPLIT3>(hi, lo, row, c0 + c,
                           make_float4(f.v[c * 4], f.v[c * 4 + 1], f.v[c * 4 + 2], f.v[c * 4 + 3]));
   }
-  static __device__ __forceinline__ void load_b(const Params& p, const uint8_t*, int n0, int kb, int t, BFrag& f) {
+  static __device__ __forceinline__ void load_b(const Params& p, const BState&, const uint8_t*, int n0, int kb, int t, BFrag& f) {
     // B[ci][k = (co,ky,kx)] = wt[((co*Cin + ci)*K + ky)*K + kx]
     const int KK = p.K * p.K;
     load_weights<BN, 32 * NB>(f, t, [&](int row, int kk) {
@@ -245,7 +249,7 @@ struct ConvDgradProblem {
       return (ci < p.Cin && k < p.red) ? __ldg(p.wt + ((long long)co * p.Cin + ci) * KK + r) : 0.0f;
     });
   }
-  static __device__ __forceinline__ void store_b(const Params&, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+  static __device__ __forceinline__ void store_b(const Params&, const BState&, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
     store_weights<BN, SPLIT3, 32 * NB>(f, hi, lo, t);
   }
   template <int HALF>
@@ -285,6 +289,8 @@ struct ConvWgradProblem {
   // lane <-> pixel of the k-block; warp w walks over its 16 tap rows
   using AFrag = Frag<16>;
   using BFrag = Frag<BN / 4>;
+  struct BState {};
+  static __device__ __forceinline__ void b_setup(const Params&, const uint8_t*, int, int, BState&) {}
   static __device__ __forceinline__ void load_a(const Params& p, const AState&, const uint8_t* scratch,
                                                 int m0, int kb, int t, AFrag& f) {
     const int lane = t & 31, w = t >> 5;
@@ -300,12 +306,12 @@ struct ConvWgradProblem {
 #pragma unroll
     for (int rr = 0; rr < 16; ++rr) f.v[rr] = xrow_load(p, xr, tab[rr]);
   }
-  static __device__ __forceinline__ void store_a(const Params&, const AFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+  static __device__ __forceinline__ void store_a(const Params&, const AState&, const AFrag& f, uint8_t* hi, uint8_t* lo, int t) {
     const int lane = t & 31, w = t >> 5;
 #pragma unroll
     for (int rr = 0; rr < 16; ++rr) store_elem<SPLIT3>(hi, lo, w * 16 + rr, lane, f.v[rr]);
   }
-  static __device__ __forceinline__ void load_b(const Params& p, const uint8_t*, int n0, int kb, int t, BFrag& f) {
+  static __device__ __forceinline__ void load_b(const Params& p, const BState&, const uint8_t*, int n0, int kb, int t, BFrag& f) {
     const int lane = t & 31, w = t >> 5;
     const long long px = (long long)kb * KB + lane;
     const bool pok = px < p.red;
@@ -320,7 +326,7 @@ struct ConvWgradProblem {
       f.v[rr] = (pok && co < p.Cout) ? __ldg(src + (long long)co * ohw) : 0.0f;
     }
   }
-  static __device__ __forceinline__ void store_b(const Params&, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
+  static __device__ __forceinline__ void store_b(const Params&, const BState&, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
     const int lane = t & 31, w = t >> 5;
     constexpr int RW = BN / NB;
 #pragma unroll

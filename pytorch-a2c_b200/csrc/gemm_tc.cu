@@ -21,10 +21,25 @@ struct GemmOperand {
   const float* p;
   long long s_mn, s_k;
   int mode;   // 0: k contiguous, 1: mn contiguous
+  int dbg;
 };
 
-__device__ __forceinline__ float4 gemm_ld4(const GemmOperand& op, long long off) {
-  return __ldg(reinterpret_cast<const float4*>(op.p + off));
+__device__ __forceinline__ float4 gemm_ld4(const GemmOperand& op, const float* a) {
+#ifdef A2C_DEBUG_KNOBS
+  float4 v;
+  if ((op.dbg & 3) == 1) {
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a));
+    return v;
+  } else if ((op.dbg & 3) == 2) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a));
+    return v;
+  } else if ((op.dbg & 3) == 3) {
+    asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a));
+    return v;
+  }
+  if (op.dbg & 8) return make_float4(1.f, 2.f, 3.f, 4.f);
+#endif
+  return __ldg(reinterpret_cast<const float4*>(a));
 }
 
 struct GemmParams {
@@ -55,51 +70,88 @@ struct GemmFrag {
 __device__ __forceinline__ int mn_group(int t) { return (((t >> 3) & 3) << 1) | (t & 1) | (((t >> 5) & 3) << 3); }
 __device__ __forceinline__ int k_chunk(int t) { return ((t >> 1) & 3) | ((t >> 7) << 2); }
 
-// Load phase: global -> registers.  t = thread index within the operand's producers.
+// Per-thread producer state of one operand for the current tile: everything that does not depend on
+// the k-block is computed once per tile (the producers are issue-bound: with the row decode, bounds
+// checks and 64-bit address arithmetic inside the k loop every 128-bit load cost ~40 instructions).
+struct GemmRowState {
+  const float* base;   // first element this thread loads at k-block 0
+  long long step;      // mode 0: elements between this thread's units (32 rows); mode 1: s_k
+  int kfirst;          // k of the thread's first element inside a k-block
+  int valid;           // mode 0: bit i = unit i is a row of the matrix; mode 1: the 4-row group is
+  int soff;            // byte offset of the thread's first store inside the swizzled tile (tile-independent)
+};
+
 template <int ROWS>
-__device__ __forceinline__ void gemm_load(const GemmOperand& op, int MN, int K, int mn0, int k0, int t,
-                                          GemmFrag<ROWS>& f) {
+__device__ __forceinline__ void gemm_setup(const GemmOperand& op, int MN, int mn0, int t, GemmRowState& st) {
   if (op.mode == 0) {
-    // k contiguous: unit = (row, 16-byte chunk); a quarter-warp covers one row's 128 bytes
+    // k contiguous: unit i = (row (t >> 3) + 32 i, 16-byte chunk t & 7); a quarter-warp covers one row's 128 bytes
+    const int row = t >> 3, chunk = t & 7;
+    st.kfirst = chunk * 4;
+    st.base = op.p + (long long)(mn0 + row) * op.s_mn + st.kfirst;
+    st.step = 32 * op.s_mn;
+    st.valid = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int u = i * PROD_THREADS + t, row = u >> 3, chunk = u & 7;
-      const int mn = mn0 + row, k = k0 + chunk * 4;
-      f.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < ROWS && mn < MN && k < K) f.v[i] = gemm_ld4(op, (long long)mn * op.s_mn + k);
-    }
+    for (int i = 0; i < 4; ++i)
+      if (row + 32 * i < ROWS && mn0 + row + 32 * i < MN) st.valid |= 1 << i;
+    st.soff = swz(row, chunk);           // unit i: + 4096 i (32 rows; row & 7 does not change)
   } else {
     // mn contiguous: unit = (group of 4 rows, k-chunk): 4 loads along mn (transposed at store time).
     // 8 consecutive lanes take 8 consecutive groups, so a warp load covers 4 k-rows x 128 contiguous bytes
     const int g = mn_group(t), chunk = k_chunk(t);
-    const int mn = mn0 + g * 4;
+    st.kfirst = chunk * 4;
+    st.base = op.p + (long long)st.kfirst * op.s_k + mn0 + g * 4;
+    st.step = op.s_k;
+    st.valid = (g * 4 < ROWS && mn0 + g * 4 < MN) ? 1 : 0;
+    // row g*4 + q, chunk ^ (row & 7):  (row & 7) = ((g & 1) << 2) | q, so store q sits at
+    // ((soff ^ (q << 4)) + 128 q)
+    st.soff = g * 512 + ((chunk ^ ((g & 1) << 2)) << 4);
+  }
+}
+
+// Load phase: global -> registers.
+template <int ROWS>
+__device__ __forceinline__ void gemm_load(const GemmOperand& op, const GemmRowState& st, int K, int k0,
+                                          GemmFrag<ROWS>& f) {
+  if (op.mode == 0) {
+    const float* src = st.base + k0;
+    const bool kok = k0 + st.kfirst < K;          // K % 4 == 0 (classify)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kok && ((st.valid >> i) & 1)) f.v[i] = gemm_ld4(op, src + i * st.step);
+    }
+  } else {
+    const float* src = st.base + (long long)k0 * st.step;
+    const int krem = K - k0 - st.kfirst;          // rows of k left for this thread
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int k = k0 + chunk * 4 + j;
       f.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g * 4 < ROWS && mn < MN && k < K) f.v[j] = gemm_ld4(op, (long long)k * op.s_k + mn);
+      if (st.valid && j < krem) f.v[j] = gemm_ld4(op, src + j * st.step);
     }
   }
 }
 
 // Store phase: registers -> swizzled tile(s), with the hi/lo split.
 template <int ROWS, bool SPLIT3>
-__device__ __forceinline__ void gemm_store(const GemmOperand& op, const GemmFrag<ROWS>& f, uint8_t* hi,
-                                           uint8_t* lo, int t) {
+__device__ __forceinline__ void gemm_store(const GemmOperand& op, const GemmRowState& st, const GemmFrag<ROWS>& f,
+                                           uint8_t* hi, uint8_t* lo, int t) {
+#ifdef A2C_DEBUG_KNOBS
+  if (op.dbg & 16) {
+    if (f.v[0].x == 1.2345f && f.v[1].y == 3.21f && f.v[2].x == 7.7f && f.v[3].x == 1.1f) *hi = 1;
+    return;
+  }
+#endif
   if (op.mode == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int u = i * PROD_THREADS + t;
-      if ((u >> 3) < ROWS) store_chunk<SPLIT3>(hi, lo, u >> 3, u & 7, f.v[i]);
-    }
+    for (int i = 0; i < 4; ++i)
+      if ((t >> 3) + 32 * i < ROWS) store_chunk_at<SPLIT3>(hi, lo, st.soff + 4096 * i, f.v[i]);
   } else {
-    const int g = mn_group(t), chunk = k_chunk(t);
-    if (g * 4 < ROWS) {
+    if (mn_group(t) * 4 < ROWS) {
       const float4* v = f.v;
-      store_chunk<SPLIT3>(hi, lo, g * 4 + 0, chunk, make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
-      store_chunk<SPLIT3>(hi, lo, g * 4 + 1, chunk, make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
-      store_chunk<SPLIT3>(hi, lo, g * 4 + 2, chunk, make_float4(v[0].z, v[1].z, v[2].z, v[3].z));
-      store_chunk<SPLIT3>(hi, lo, g * 4 + 3, chunk, make_float4(v[0].w, v[1].w, v[2].w, v[3].w));
+      store_chunk_at<SPLIT3>(hi, lo, st.soff, make_float4(v[0].x, v[1].x, v[2].x, v[3].x));
+      store_chunk_at<SPLIT3>(hi, lo, (st.soff ^ 16) + 128, make_float4(v[0].y, v[1].y, v[2].y, v[3].y));
+      store_chunk_at<SPLIT3>(hi, lo, (st.soff ^ 32) + 256, make_float4(v[0].z, v[1].z, v[2].z, v[3].z));
+      store_chunk_at<SPLIT3>(hi, lo, (st.soff ^ 48) + 384, make_float4(v[0].w, v[1].w, v[2].w, v[3].w));
     }
   }
 }
@@ -113,23 +165,32 @@ struct GemmProblem {
   using Params = GemmParams;
   // 16 producer warps, loads two k-blocks ahead: 64 KB of operand loads in flight per SM
   static constexpr int NA = 8, NB = 8, KC = KCHAIN, DEPTH = 2;
-  struct AState {};
+  using AState = GemmRowState;
+  using BState = GemmRowState;
   using AFrag = GemmFrag<TM>;
   using BFrag = GemmFrag<BN>;
   static __device__ __forceinline__ void init(const Params&, uint8_t*, int, int) {}
-  static __device__ __forceinline__ void a_setup(const Params&, const uint8_t*, int, int, AState&) {}
-  static __device__ __forceinline__ void load_a(const Params& p, const AState&, const uint8_t*, int m0, int kb,
-                                                int t, AFrag& f) {
-    gemm_load<TM>(p.A, p.M, p.K, m0, kb * KB, t, f);
+  static __device__ __forceinline__ void a_setup(const Params& p, const uint8_t*, int m0, int t, AState& st) {
+    gemm_setup<TM>(p.A, p.M, m0, t, st);
   }
-  static __device__ __forceinline__ void store_a(const Params& p, const AFrag& f, uint8_t* hi, uint8_t* lo, int t) {
-    gemm_store<TM, SPLIT3>(p.A, f, hi, lo, t);
+  static __device__ __forceinline__ void b_setup(const Params& p, const uint8_t*, int n0, int t, BState& st) {
+    gemm_setup<BN>(p.B, p.N, n0, t, st);
   }
-  static __device__ __forceinline__ void load_b(const Params& p, const uint8_t*, int n0, int kb, int t, BFrag& f) {
-    gemm_load<BN>(p.B, p.N, p.K, n0, kb * KB, t, f);
+  static __device__ __forceinline__ void load_a(const Params& p, const AState& st, const uint8_t*, int, int kb,
+                                                int, AFrag& f) {
+    gemm_load<TM>(p.A, st, p.K, kb * KB, f);
   }
-  static __device__ __forceinline__ void store_b(const Params& p, const BFrag& f, uint8_t* hi, uint8_t* lo, int t) {
-    gemm_store<BN, SPLIT3>(p.B, f, hi, lo, t);
+  static __device__ __forceinline__ void store_a(const Params& p, const AState& st, const AFrag& f, uint8_t* hi,
+                                                 uint8_t* lo, int t) {
+    gemm_store<TM, SPLIT3>(p.A, st, f, hi, lo, t);
+  }
+  static __device__ __forceinline__ void load_b(const Params& p, const BState& st, const uint8_t*, int, int kb,
+                                                int, BFrag& f) {
+    gemm_load<BN>(p.B, st, p.K, kb * KB, f);
+  }
+  static __device__ __forceinline__ void store_b(const Params& p, const BState& st, const BFrag& f, uint8_t* hi,
+                                                 uint8_t* lo, int t) {
+    gemm_store<BN, SPLIT3>(p.B, st, f, hi, lo, t);
   }
   template <int HALF>
   static __device__ __forceinline__ void epilogue(const Params& p, int row, int nb, const float* acc, int split) {
@@ -215,6 +276,7 @@ int gemm_tc_try(const float* A, long long sam, long long sak, const float* B, lo
   if (!tc::classify(B, sbn, sbk, N, K, &p.B)) return 1;
   p.C = C; p.ldc = ldc; p.bias = bias; p.M = M; p.N = N; p.K = K; p.relu = relu; p.beta = beta;
   p.cmask = cmask;
+  p.A.dbg = p.B.dbg = debug_knob("A2C_GEMM_DBG");
   p.nkb = cdiv(K, tc::KB); p.kb_per_split = p.nkb;
   const bool split3 = (precision == 1);
   int bn = N > 64 ? 128 : (N > 32 ? 64 : 32);

@@ -108,19 +108,20 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Round to nearest (even) TF32: ONE instruction (F2FP.TF32.F32, full rate).  cvt.rna (ties away) has
+// no hardware form on sm_100a -- ptxas emulates it with FSETP + IADD + SEL + LOP3 per element, which
+// made the operand producers issue-bound (ncu: 29 % of the GEMM's instructions were that emulation).
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
 
 __device__ __forceinline__ int swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
-// Stores one 16-byte chunk (4 consecutive k of one row) into the swizzled tile(s).
+// Stores one 16-byte chunk (4 consecutive k of one row) at byte offset `off` = swz(row, chunk) of the tile(s).
 template <bool SPLIT3>
-__device__ __forceinline__ void store_chunk(uint8_t* hi_tile, uint8_t* lo_tile, int row, int chunk,
-                                            float4 v) {
-  const int off = swz(row, chunk);
+__device__ __forceinline__ void store_chunk_at(uint8_t* hi_tile, uint8_t* lo_tile, int off, float4 v) {
   if constexpr (SPLIT3) {
     float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
     *reinterpret_cast<float4*>(hi_tile + off) = h;
@@ -131,6 +132,11 @@ __device__ __forceinline__ void store_chunk(uint8_t* hi_tile, uint8_t* lo_tile, 
   } else {
     *reinterpret_cast<float4*>(hi_tile + off) = v;
   }
+}
+template <bool SPLIT3>
+__device__ __forceinline__ void store_chunk(uint8_t* hi_tile, uint8_t* lo_tile, int row, int chunk,
+                                            float4 v) {
+  store_chunk_at<SPLIT3>(hi_tile, lo_tile, swz(row, chunk), v);
 }
 
 // Stores one element (row, k) into the swizzled tile(s).
@@ -151,11 +157,14 @@ __device__ __forceinline__ void store_elem(uint8_t* hi_tile, uint8_t* lo_tile, i
 //   static constexpr int KC;          k-blocks chained in one TMEM accumulator before it is drained
 //   static constexpr int DEPTH;       k-blocks the producers' global loads run ahead of their stores (1 or 2)
 //   struct Params { ...; int nkb; int kb_per_split; };        (nkb = total k-blocks)
-//   struct AState;                    per-thread, per-m-tile producer state (row decode etc.)
+//   struct AState, BState;            per-thread producer state of the current m / n tile (row decode etc.);
+//                                     the stores may lag one tile behind the loads, so whatever store_a /
+//                                     store_b read from the state must not depend on the tile
 //   static __device__ void init(const Params&, uint8_t* scratch, int tid, int nthreads);
 //   static __device__ void a_setup(const Params&, const uint8_t* scratch, int m0, int t, AState&);
-//   static __device__ void produce_a(const Params&, const AState&, const uint8_t* scratch, int m0, int kb, hi, lo, int t);
-//   static __device__ void produce_b(const Params&, const uint8_t* scratch, int n0, int kb, hi, lo, int t);
+//   static __device__ void b_setup(const Params&, const uint8_t* scratch, int n0, int t, BState&);
+//   static __device__ void load_a / load_b(const Params&, const State&, scratch, int mn0, int kb, int t, Frag&);
+//   static __device__ void store_a / store_b(const Params&, const State&, const Frag&, hi, lo, int t);
 //   static __device__ void epilogue<HALF>(const Params&, int m, int n_begin, const float* acc, int split);
 // t = thread index within the operand's producer warps.
 template <int BN, bool SPLIT3, class P>
@@ -259,7 +268,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
         const int s = ring.s;
         mbar_wait(&empty[s], ring.par ^ 1);
         uint8_t* st = stage_ptr(s);
-        P::store_a(p, f0, st, st + A_BYTES, t);
+        P::store_a(p, ast, f0, st, st + A_BYTES, t);
         fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
@@ -274,17 +283,23 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
     const int t = (int)threadIdx.x - 32 * P::NA;
     StageRing ring(stages);
     if (tile0 < total_tiles && nkb > 0) {
+      typename P::BState bst;
       typename P::BFrag f0, f1, f2;
       int s_tile = tile0, s_i = 0;
       int l_tile = tile0, l_i = 0, l_mt, l_nt;
       tile_of(l_tile, l_mt, l_nt);
+      P::b_setup(p, scratch, l_nt * BN, t, bst);
       auto load_next = [&](typename P::BFrag& f) {
         if (l_tile >= total_tiles) return;
-        P::load_b(p, scratch, l_nt * BN, kb_begin + l_i, t, f);
+        P::load_b(p, bst, scratch, l_nt * BN, kb_begin + l_i, t, f);
         if (++l_i == nkb) {
           l_i = 0;
           l_tile += tile_step;
-          if (l_tile < total_tiles) tile_of(l_tile, l_mt, l_nt);
+          if (l_tile < total_tiles) {
+            int nt2;
+            tile_of(l_tile, l_mt, nt2);
+            if (nt2 != l_nt) { l_nt = nt2; P::b_setup(p, scratch, l_nt * BN, t, bst); }
+          }
         }
       };
       load_next(f0);
@@ -294,7 +309,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
         const int s = ring.s;
         mbar_wait(&empty[s], ring.par ^ 1);
         uint8_t* b = stage_ptr(s) + (SPLIT3 ? 2 : 1) * A_BYTES;
-        P::store_b(p, f0, b, b + B_BYTES, t);
+        P::store_b(p, bst, f0, b, b + B_BYTES, t);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
@@ -359,7 +374,8 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
     for (int j = 0; j < HALF; ++j) acc[j] = 0.0f;
     for (int chunk = 0; chunk < nchunks; ++chunk, ++gchunk) {
       const int buf = gchunk & 1;
-      mbar_wait_relaxed(&acc_full[buf], (gchunk >> 1) & 1);
+      // a chunk of KC k-blocks takes microseconds: long suspend hint / sleep between polls
+      mbar_wait_relaxed(&acc_full[buf], (gchunk >> 1) & 1, KC >= 8 ? 400 : 64);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * BN + hsel * HALF;
 #pragma unroll
