@@ -74,10 +74,10 @@ __device__ __forceinline__ int k_chunk(int t) { return ((t >> 1) & 3) | ((t >> 7
 // the k-block is computed once per tile (the producers are issue-bound: with the row decode, bounds
 // checks and 64-bit address arithmetic inside the k loop every 128-bit load cost ~40 instructions).
 struct GemmRowState {
-  const float* base;   // first element this thread loads at k-block 0
-  long long step;      // mode 0: elements between this thread's units (32 rows); mode 1: s_k
+  const char* base;    // first byte this thread loads at k-block 0
+  long long step;      // BYTES between the thread's four loads: mode 0: 32 rows; mode 1: one k-row
   int kfirst;          // k of the thread's first element inside a k-block
-  int valid;           // mode 0: bit i = unit i is a row of the matrix; mode 1: the 4-row group is
+  int valid;           // mode 0: bit i = unit i is a row of the matrix; mode 1: the 4-row group is (0 / 15)
   int soff;            // byte offset of the thread's first store inside the swizzled tile (tile-independent)
 };
 
@@ -87,8 +87,8 @@ __device__ __forceinline__ void gemm_setup(const GemmOperand& op, int MN, int mn
     // k contiguous: unit i = (row (t >> 3) + 32 i, 16-byte chunk t & 7); a quarter-warp covers one row's 128 bytes
     const int row = t >> 3, chunk = t & 7;
     st.kfirst = chunk * 4;
-    st.base = op.p + (long long)(mn0 + row) * op.s_mn + st.kfirst;
-    st.step = 32 * op.s_mn;
+    st.base = reinterpret_cast<const char*>(op.p + (long long)(mn0 + row) * op.s_mn + st.kfirst);
+    st.step = 32 * op.s_mn * (long long)sizeof(float);
     st.valid = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -99,35 +99,38 @@ __device__ __forceinline__ void gemm_setup(const GemmOperand& op, int MN, int mn
     // 8 consecutive lanes take 8 consecutive groups, so a warp load covers 4 k-rows x 128 contiguous bytes
     const int g = mn_group(t), chunk = k_chunk(t);
     st.kfirst = chunk * 4;
-    st.base = op.p + (long long)st.kfirst * op.s_k + mn0 + g * 4;
-    st.step = op.s_k;
-    st.valid = (g * 4 < ROWS && mn0 + g * 4 < MN) ? 1 : 0;
+    st.base = reinterpret_cast<const char*>(op.p + (long long)st.kfirst * op.s_k + mn0 + g * 4);
+    st.step = op.s_k * (long long)sizeof(float);
+    st.valid = (g * 4 < ROWS && mn0 + g * 4 < MN) ? 15 : 0;
     // row g*4 + q, chunk ^ (row & 7):  (row & 7) = ((g & 1) << 2) | q, so store q sits at
     // ((soff ^ (q << 4)) + 128 q)
     st.soff = g * 512 + ((chunk ^ ((g & 1) << 2)) << 4);
   }
 }
 
-// Load phase: global -> registers.
+// Load phase: global -> registers.  Byte pointers, one 64-bit add per load, and a fast path without
+// predicates for the interior of the matrix: about 15 instructions for the four 128-bit loads.
 template <int ROWS>
 __device__ __forceinline__ void gemm_load(const GemmOperand& op, const GemmRowState& st, int K, int k0,
                                           GemmFrag<ROWS>& f) {
-  if (op.mode == 0) {
-    const float* src = st.base + k0;
-    const bool kok = k0 + st.kfirst < K;          // K % 4 == 0 (classify)
+  // rows of k this thread may touch in this k-block (mode 0 needs one: its chunk; mode 1 needs four)
+  const int krem = K - k0 - st.kfirst;
+  const char* src = st.base + (op.mode == 0 ? (long long)k0 * (long long)sizeof(float) : (long long)k0 * st.step);
+  if (st.valid == 15 && krem >= 4) {
+    const char* s1 = src + st.step;
+    const char* s2 = s1 + st.step;
+    const char* s3 = s2 + st.step;
+    f.v[0] = gemm_ld4(op, reinterpret_cast<const float*>(src));
+    f.v[1] = gemm_ld4(op, reinterpret_cast<const float*>(s1));
+    f.v[2] = gemm_ld4(op, reinterpret_cast<const float*>(s2));
+    f.v[3] = gemm_ld4(op, reinterpret_cast<const float*>(s3));
+    return;
+  }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      f.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kok && ((st.valid >> i) & 1)) f.v[i] = gemm_ld4(op, src + i * st.step);
-    }
-  } else {
-    const float* src = st.base + (long long)k0 * st.step;
-    const int krem = K - k0 - st.kfirst;          // rows of k left for this thread
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      f.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (st.valid && j < krem) f.v[j] = gemm_ld4(op, src + j * st.step);
-    }
+  for (int i = 0; i < 4; ++i) {
+    f.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool ok = op.mode == 0 ? (krem > 0 && ((st.valid >> i) & 1)) : (st.valid != 0 && i < krem);
+    if (ok) f.v[i] = gemm_ld4(op, reinterpret_cast<const float*>(src + i * st.step));
   }
 }
 
@@ -319,3 +322,9 @@ int gemm_tc_try(const float* A, long long sam, long long sak, const float* B, lo
 }
 
 }  // namespace a2c
+
+#ifdef A2C_TC_TRACE
+extern "C" int a2c_debug_tc_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, a2c::tc::g_tc_trace, sizeof(a2c::tc::g_tc_trace));
+}
+#endif

@@ -36,6 +36,16 @@ constexpr int TILE_GROUP_M = 8;     // m-tiles per band of the grouped tile orde
 constexpr int SCRATCH_BYTES = 4096;  // per-CTA scratch handed to Problem::init
 constexpr int MAX_THREADS = 800;     // up to 16 producer warps + 8 drain + MMA
 
+#ifdef A2C_TC_TRACE
+static __device__ long long g_tc_trace[4][64][6];
+#define TCT(role, it, ev)                                                                   \
+  do {                                                                                      \
+    if (blockIdx.x == 0 && lane == 0 && (it) >= 200 && (it) < 264) g_tc_trace[role][(it)-200][ev] = clock64(); \
+  } while (0)
+#else
+#define TCT(role, it, ev) do { } while (0)
+#endif
+
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -261,21 +271,48 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
           }
         }
       };
-      load_next(f0);
-      if constexpr (P::DEPTH == 2) load_next(f1);
-      while (s_tile < total_tiles) {
-        if constexpr (P::DEPTH == 2) load_next(f2); else load_next(f1);
+      // one k-block: start the loads of the k-block DEPTH ahead into `fl`, convert and store `fs`.
+      // The loop below is unrolled over the DEPTH + 1 fragments so that they rotate by NAME (a
+      // `f0 = f1; f1 = f2` rotation cost 32 register moves per k-block in an issue-bound loop).
+      int kit = 0;
+      // one k-block: convert and store fragment `f`, then refill the same registers with the k-block
+      // DEPTH + 1 ahead.  The loads are issued AFTER the stores: issued before them, they shared a
+      // hardware scoreboard with the fragment being consumed in one of the three unrolled copies and
+      // every third k-block waited a full memory latency (clock trace: 1,400-1,900 clk instead of 300).
+      auto step = [&](typename P::AFrag& f) -> bool {
+        TCT(0, kit, 0);
         const int s = ring.s;
         mbar_wait(&empty[s], ring.par ^ 1);
+        TCT(0, kit, 1);
         uint8_t* st = stage_ptr(s);
-        P::store_a(p, ast, f0, st, st + A_BYTES, t);
+        P::store_a(p, ast, f, st, st + A_BYTES, t);
+        TCT(0, kit, 2);
         fence_proxy_async();      // generic-proxy stores -> visible to the tensor core (async proxy)
+        TCT(0, kit, 3);
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
-        f0 = f1;
-        if constexpr (P::DEPTH == 2) f1 = f2;
+        TCT(0, kit, 4);
+        load_next(f);
+        TCT(0, kit, 5);
+        if (warp == 0) ++kit;
         if (++s_i == nkb) { s_i = 0; s_tile += tile_step; }
         ring.next();
+        return s_tile < total_tiles;
+      };
+      load_next(f0);
+      load_next(f1);
+      if constexpr (P::DEPTH == 2) {
+        load_next(f2);
+        for (;;) {
+          if (!step(f0)) break;
+          if (!step(f1)) break;
+          if (!step(f2)) break;
+        }
+      } else {
+        for (;;) {
+          if (!step(f0)) break;
+          if (!step(f1)) break;
+        }
       }
     }
   } else if (warp < NUM_PROD_WARPS) {
@@ -302,21 +339,41 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
           }
         }
       };
-      load_next(f0);
-      if constexpr (P::DEPTH == 2) load_next(f1);
-      while (s_tile < total_tiles) {
-        if constexpr (P::DEPTH == 2) load_next(f2); else load_next(f1);
+      int kit = 0;
+      auto step = [&](typename P::BFrag& f) -> bool {
+        TCT(1, kit, 0);
         const int s = ring.s;
         mbar_wait(&empty[s], ring.par ^ 1);
+        TCT(1, kit, 1);
         uint8_t* b = stage_ptr(s) + (SPLIT3 ? 2 : 1) * A_BYTES;
-        P::store_b(p, bst, f0, b, b + B_BYTES, t);
+        P::store_b(p, bst, f, b, b + B_BYTES, t);
+        TCT(1, kit, 2);
         fence_proxy_async();
+        TCT(1, kit, 3);
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[s]);
-        f0 = f1;
-        if constexpr (P::DEPTH == 2) f1 = f2;
+        TCT(1, kit, 4);
+        load_next(f);
+        TCT(1, kit, 5);
+        if (warp == P::NA) ++kit; else kit = -1;
         if (++s_i == nkb) { s_i = 0; s_tile += tile_step; }
         ring.next();
+        return s_tile < total_tiles;
+      };
+      load_next(f0);
+      load_next(f1);
+      if constexpr (P::DEPTH == 2) {
+        load_next(f2);
+        for (;;) {
+          if (!step(f0)) break;
+          if (!step(f1)) break;
+          if (!step(f2)) break;
+        }
+      } else {
+        for (;;) {
+          if (!step(f0)) break;
+          if (!step(f1)) break;
+        }
       }
     }
   } else if (warp == MMA_WARP) {
@@ -329,11 +386,14 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
       const int s = ring.s;
       const uint32_t parity = ring.par;
       const int chunk = gchunk0 + i / KC, buf = chunk & 1;
+      TCT(2, it, 0);
       if (i % KC == 0) {                        // new chunk: its TMEM buffer must have been drained
         mbar_wait(&acc_empty[buf], ((chunk >> 1) & 1) ^ 1);
         tc_fence_after();
       }
+      TCT(2, it, 1);
       mbar_wait(&full[s], parity);
+      TCT(2, it, 2);
       tc_fence_after();
       // convergent warp, one elected lane, descriptor low words in uniform registers (see
       // mma_tf32_imm): about 3 issue instructions per MMA instead of ~25
@@ -360,6 +420,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
         if (i % KC == KC - 1 || i == nkb - 1) mma_commit(&acc_full[buf]);   // chunk complete
       }
       __syncwarp();
+      TCT(2, it, 3);
     }
   } else if (warp >= EPI0 && warp < EPI0 + NUM_EPI_WARPS) {
     // ---- drain + epilogue: thread <-> accumulator row (TMEM lane), half of the columns ----
@@ -374,8 +435,15 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
     for (int j = 0; j < HALF; ++j) acc[j] = 0.0f;
     for (int chunk = 0; chunk < nchunks; ++chunk, ++gchunk) {
       const int buf = gchunk & 1;
-      // a chunk of KC k-blocks takes microseconds: long suspend hint / sleep between polls
-      mbar_wait_relaxed(&acc_full[buf], (gchunk >> 1) & 1, KC >= 8 ? 400 : 64);
+      // Only ONE drain warp watches the mbarrier; the other seven park at a named hardware barrier.
+      // A warp waiting on an mbarrier is woken by every arrival on any mbarrier of the CTA (17 per
+      // k-block here) and re-polls: ncu showed the eight drain warps spending a quarter of the SM's
+      // issue slots on that while the producers were issue-bound.
+      if (e == 0) { TCT(3, 200 + gchunk, 0); }
+      if (e == 0) mbar_wait_relaxed(&acc_full[buf], (gchunk >> 1) & 1, KC >= 8 ? 400 : 64);
+      if (e == 0) { TCT(3, 200 + gchunk, 1); }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
+      if (e == 0) { TCT(3, 200 + gchunk, 2); }
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * BN + hsel * HALF;
 #pragma unroll
@@ -407,6 +475,7 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (e == 0) { TCT(3, 200 + gchunk, 3); }
     }
     P::template epilogue<HALF>(p, m0 + q * 32 + lane, n0 + hsel * HALF, acc, (int)blockIdx.z);
     }
