@@ -24,7 +24,7 @@ def main(src, out):
          "gradient entry); the float64 oracle is evaluated on the GPU's fp64 units and first pinned (2e-7) to the",
          "committed CPU-generated float64 fixture.  `e_sampled` = the same against the fixture's norm + 4,096 strided",
          "samples.  `ref_own` = the unmodified fp32 reference's own distance from the float64 values (same metric,",
-         "from the fixtures).  Bar: `max(1e-5, ref_own) + k * ref_own` with k = 2 (precision 0, fp32 FFMA) and k = 6",
+         "from the fixtures).  Bar: `max(1e-5, ref_own) + k * ref_own` with k = 2 (precision 0, fp32 FFMA) and k = 8",
          "(precision 1, 3xTF32 on tcgen05); `used` = e_full / bar as printed by the run that produced this file",
          "(its bar may have used an earlier k; the ratios in the section titles are what k was chosen from);",
          "`clause` = which term of the bar decides.", ""]

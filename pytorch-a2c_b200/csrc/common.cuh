@@ -155,6 +155,17 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   while (!mbar_try_wait_hint(bar, parity, ns)) __nanosleep(ns);
 }
 
+// A group of `nwarps` warps waits for the same mbarrier phase: only the group's first warp (`leader`)
+// watches the mbarrier, the others park at named hardware barrier `bar_id` (1..15, one id per group).
+// A warp waiting on an mbarrier is woken by every arrival on any mbarrier of the CTA and re-polls;
+// with 8-16 waiters that polling took 25-60 % of the instructions these kernels issued (ncu, round 2).
+// All warps of the group must call this the same number of times.
+__device__ __forceinline__ void mbar_wait_group(uint64_t* bar, uint32_t parity, bool leader, int bar_id, int nwarps,
+                                                unsigned ns = 64) {
+  if (leader) mbar_wait_relaxed(bar, parity, ns);
+  asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(32 * nwarps) : "memory");
+}
+
 // Stage index + phase parity of a circular mbarrier pipeline, advanced without div/mod.
 struct StageRing {
   int s, n;

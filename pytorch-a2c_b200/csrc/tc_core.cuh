@@ -435,15 +435,8 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
     for (int j = 0; j < HALF; ++j) acc[j] = 0.0f;
     for (int chunk = 0; chunk < nchunks; ++chunk, ++gchunk) {
       const int buf = gchunk & 1;
-      // Only ONE drain warp watches the mbarrier; the other seven park at a named hardware barrier.
-      // A warp waiting on an mbarrier is woken by every arrival on any mbarrier of the CTA (17 per
-      // k-block here) and re-polls: ncu showed the eight drain warps spending a quarter of the SM's
-      // issue slots on that while the producers were issue-bound.
-      if (e == 0) { TCT(3, 200 + gchunk, 0); }
-      if (e == 0) mbar_wait_relaxed(&acc_full[buf], (gchunk >> 1) & 1, KC >= 8 ? 400 : 64);
-      if (e == 0) { TCT(3, 200 + gchunk, 1); }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * NUM_EPI_WARPS) : "memory");
-      if (e == 0) { TCT(3, 200 + gchunk, 2); }
+      // only one drain warp watches the mbarrier (see mbar_wait_group)
+      mbar_wait_group(&acc_full[buf], (gchunk >> 1) & 1, e == 0, 1, NUM_EPI_WARPS, KC >= 8 ? 400 : 64);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 2 * BN + hsel * HALF;
 #pragma unroll

