@@ -137,6 +137,18 @@ __device__ __forceinline__ void wg_tmem_ld8(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
+// Per-role clock stamps of CTA 0 (build flag -DA2C_TC_TRACE; read back with a2c_debug_wg_trace,
+// scratch/wg_trace.py): the tool that found the GEMM's stalls (DESIGN.md lesson 19).
+#ifdef A2C_TC_TRACE
+static __device__ long long g_wg_trace[3][64][4];
+#define WGT(role, it, ev)                                                                    \
+  do {                                                                                       \
+    if (blockIdx.x == 0 && lane == 0 && (it) >= 20 && (it) < 84) g_wg_trace[role][(it)-20][ev] = clock64(); \
+  } while (0)
+#else
+#define WGT(role, it, ev) do { } while (0)
+#endif
+
 struct WgItem {
   int img, r0, rows, c0;          // image, first output row, rows, first output column of the chunk
 };
@@ -242,9 +254,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
     const int pgw = WG_PROD / p.pgroups;                    // warps per group
     const int grp = warp / pgw, pw = warp - grp * pgw;
     struct { int s; uint32_t par; } ring = {p.pgroups == 2 ? grp : 0, 0u};
-    for (int item = first_item + grp * item_step; item < nitems; item += p.pgroups * item_step) {
+    int tit = warp == 0 ? 0 : -1000000;
+    for (int item = first_item + grp * item_step; item < nitems; item += p.pgroups * item_step, ++tit) {
       const WgItem it = item_of(item);
+      WGT(0, tit, 0);
       mbar_wait_relaxed(&band_empty[ring.s], ring.par ^ 1);
+      WGT(0, tit, 1);
       if (!(p.dbg & 4)) {
       if (p.pack3) {
         // --- first layer: <= 4 channels, f32 tensor or uint8 ring view; a row's pixel goes to
@@ -393,6 +408,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         }
         }
       }
+      WGT(0, tit, 2);
       // --- dY band (masked) ---
       if (p.scalar_w) {
         uint8_t* buf = ob + (size_t)ring.s * p.o_buf;
@@ -451,6 +467,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&band_full[ring.s]);
+      WGT(0, tit, 3);
       if (p.pgroups == 2) ring.par ^= 1u;                    // same buffer again, next phase
       else if ((ring.s ^= 1) == 0) ring.par ^= 1u;           // alternate buffers
     }
@@ -468,9 +485,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
     const int ksteps = p.PWo >> 3;
     StageRing ring(2);
     uint32_t ccount = 0, slot = 0, sphase = 0;
-    for (int item = first_item; item < nitems; item += item_step, ring.next()) {
+    int tit = me == 0 ? 0 : -1000000;
+    for (int item = first_item; item < nitems; item += item_step, ring.next(), ++tit) {
       const WgItem it = item_of(item);
+      WGT(1, tit, 0);
       mbar_wait(&band_full[ring.s], ring.par);
+      WGT(1, tit, 1);
       tc_fence_after();
       const uint32_t a_buf = a_w0 + ring.s * xbuf16, b_buf = b_w0 + ring.s * obuf16;
       for (int j0 = 0; j0 < it.rows; j0 += p.rpc, ++ccount) {
@@ -523,6 +543,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         if (elect_one()) mma_commit(&acc_full[ab]);
       }
       if (elect_one()) mma_commit(&band_empty[ring.s]);
+      WGT(1, tit, 2);
     }
   } else if (warp >= WG_DRAIN0 && warp < WG_DRAIN0 + NUM_EPI_WARPS) {
     // ---------------- drain: running sums in registers ----------------
@@ -531,11 +552,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
 #pragma unroll
     for (int j = 0; j < NC; ++j) acc[j] = 0.0f;
     uint32_t slot = 0, sphase = 0;
-    for (int item = first_item; item < nitems; item += item_step) {
+    int tit = e == 0 ? 0 : -1000000;
+    for (int item = first_item; item < nitems; item += item_step, ++tit) {
       const WgItem it = item_of(item);
+      WGT(2, tit, 0);
       for (int j0 = 0; j0 < it.rows; j0 += p.rpc) {
         const uint32_t ab = slot;
         mbar_wait(&acc_full[ab], sphase);
+        if (j0 == 0) { WGT(2, tit, 1); }
         if (++slot == WG_NSLOT) { slot = 0; sphase ^= 1u; }
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * WG_TCOLS;
@@ -558,6 +582,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv_shift_wgrad_kernel(const _
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[ab]);
       }
+      WGT(2, tit, 2);
     }
     float* dst = p.partial + ((size_t)blockIdx.x * 128 + q * 32 + lane) * WG_NACC + hsel * NC;
 #pragma unroll
@@ -833,3 +858,9 @@ int conv_wgrad_shift_try(const float* X, const a2c_state_view* xview, const floa
 }
 
 }  // namespace a2c
+
+#ifdef A2C_TC_TRACE
+extern "C" int a2c_debug_wg_trace(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, a2c::tc::g_wg_trace, sizeof(a2c::tc::g_wg_trace));
+}
+#endif
