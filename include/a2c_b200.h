@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define A2C_ERR_ARG (-1)
-#define A2C_ABI_VERSION 2
+#define A2C_ABI_VERSION 3
 
 int a2c_abi_version(void);
 const char* a2c_last_error(void);
@@ -239,6 +239,20 @@ int a2c_conv2d_bwd_data_relu(const float* dY, const float* Ymask, const float* W
                              float* dX, float* dbias_prev, int N, const a2c_conv_shape* s,
                              int precision, void* workspace, long long workspace_bytes,
                              void* stream);
+/* 1-bit ReLU masks (a2c/models.py:312,685: every Conv2d of the stacks is followed by nn.ReLU).
+ * relu_bits u8 [N, Cout/8, OH*OW]: bit (c & 7) of byte [n, c >> 3, pos] = Y[n, c, pos] > 0; Cout % 8 == 0.
+ * a2c_conv2d_fwd_relu_bits = a2c_conv2d_fwd with relu = 1 that also writes the bits (in the epilogue
+ * of the tcgen05 shift-GEMM; any other path runs the plain forward and one pass over Y).
+ * a2c_conv2d_bwd_data_relu_bits = a2c_conv2d_bwd_data_relu whose epilogue reads Xbits (the bits of the
+ * layer that produced X) instead of the fp32 X: one byte per 8 channels and position instead of eight
+ * strided floats.  X is still passed: paths without the fused epilogue mask with it. */
+int a2c_conv2d_fwd_relu_bits(const float* X, const a2c_state_view* xview, const float* Wt,
+                             const float* bias, float* Y, unsigned char* relu_bits, int N,
+                             const a2c_conv_shape* s, int precision, void* stream);
+int a2c_conv2d_bwd_data_relu_bits(const float* dY, const float* Ymask, const float* Wt, const float* X,
+                                  const unsigned char* Xbits, float* dX, float* dbias_prev, int N,
+                                  const a2c_conv_shape* s, int precision, void* workspace,
+                                  long long workspace_bytes, void* stream);
 /* out f32 [C] = per-channel sums of X f32 [N, C, HW] where mask > 0 (mask may be NULL): the bias
  * gradient of the last conv layer from its masked output gradient.  workspace >= 8*C bytes. */
 int a2c_channel_sum(const float* X, const float* mask, float* out, int N, int C, int HW,

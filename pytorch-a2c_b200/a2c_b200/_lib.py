@@ -71,6 +71,8 @@ SIGNATURES = {
     "a2c_conv2d_fwd": [_p, _SV, _p, _p, _p, _i, _CS, _i, _i, _p],
     "a2c_conv2d_bwd_data": [_p, _p, _p, _p, _i, _CS, _i, _p],
     "a2c_conv2d_bwd_data_relu": [_p, _p, _p, _p, _p, _p, _i, _CS, _i, _p, _ll, _p],
+    "a2c_conv2d_fwd_relu_bits": [_p, _SV, _p, _p, _p, _p, _i, _CS, _i, _p],
+    "a2c_conv2d_bwd_data_relu_bits": [_p, _p, _p, _p, _p, _p, _p, _i, _CS, _i, _p, _ll, _p],
     "a2c_channel_sum": [_p, _p, _p, _i, _i, _i, _p, _ll, _p],
     "a2c_conv2d_last_path": [],
     "a2c_conv2d_fused_mask": [_CS, _i, _i],

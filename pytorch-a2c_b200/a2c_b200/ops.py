@@ -513,7 +513,7 @@ class ConvStackFn(torch.autograd.Function):
         L = len(geom)
         assert len(params) == 2 * L
         is_view = isinstance(x, View)
-        acts, shapes = [], []
+        acts, shapes, bitmasks = [], [], []
         cur = x
         for l in range(L):
             W, b = params[2 * l], params[2 * l + 1]
@@ -531,9 +531,24 @@ class ConvStackFn(torch.autograd.Function):
             flops = 2.0 * N * s.OH * s.OW * Cout * Cin * K * K
             sig = "%d:%d>%d,%dx%d,k%ds%d" % (N, Cin, Cout, Hh, Ww, K, stride)
             first_view = l == 0 and is_view
-            call("a2c_conv2d_fwd", None if first_view else ptr(cur), C.byref(cur.c) if first_view else None,
-                 ptr(W), ptr(b), ptr(y), N, C.byref(s), 1, _PRECISION, stream_ptr(),
-                 tag="a2c_conv2d_fwd|flops|" + sig, work=flops)
+            # A layer whose ReLU mask will be applied "at the source" in backward (same rule as there: its
+            # weight-gradient kernel has no free operand slot for the bias row) also leaves a 1-bit copy of
+            # the mask: the masked epilogue of the layer above then reads one byte per 8 channels and
+            # position instead of eight strided floats of Y.
+            bits = None
+            if l < L - 1 and Cout % 8 == 0 and any(ctx.needs_input_grad):
+                fm = call("a2c_conv2d_fused_mask", C.byref(s), _PRECISION, 1 if first_view else 0)
+                if not (fm & 4):
+                    bits = torch.empty((N, Cout // 8, s.OH * s.OW), dtype=torch.uint8, device=W.device)
+            if bits is not None:
+                call("a2c_conv2d_fwd_relu_bits", None if first_view else ptr(cur),
+                     C.byref(cur.c) if first_view else None, ptr(W), ptr(b), ptr(y), ptr(bits), N, C.byref(s),
+                     _PRECISION, stream_ptr(), tag="a2c_conv2d_fwd|flops|" + sig, work=flops)
+            else:
+                call("a2c_conv2d_fwd", None if first_view else ptr(cur), C.byref(cur.c) if first_view else None,
+                     ptr(W), ptr(b), ptr(y), N, C.byref(s), 1, _PRECISION, stream_ptr(),
+                     tag="a2c_conv2d_fwd|flops|" + sig, work=flops)
+            bitmasks.append(bits)
             _warn_if_ffma("forward", sig, _PRECISION)
             shapes.append((s, flops, sig))
             acts.append(y)
@@ -541,6 +556,7 @@ class ConvStackFn(torch.autograd.Function):
         ctx.shapes, ctx.N, ctx.L = shapes, N, L
         ctx.premasked, ctx.precision, ctx.is_view = premasked, _PRECISION, is_view
         ctx.view = x if is_view else None
+        ctx.bitmasks = bitmasks
         ctx.save_for_backward(*(([] if is_view else [x]) + acts + list(params[0::2])))
         return acts[-1]
 
@@ -601,9 +617,15 @@ class ConvStackFn(torch.autograd.Function):
                 at_source = not free_bias[l - 1]
                 if at_source:
                     dbp = torch.empty(s.Cin, dtype=torch.float32, device=dev)
-                    call("a2c_conv2d_bwd_data_relu", ptr(dy), ptr(mask), ptr(W), ptr(xin), ptr(dx), ptr(dbp), N,
-                         C.byref(s), prec, ptr(ws), ws.numel(), stream_ptr(),
-                         tag="a2c_conv2d_bwd_data|flops|" + sig, work=flops)
+                    xbits = ctx.bitmasks[l - 1]
+                    if xbits is not None:
+                        call("a2c_conv2d_bwd_data_relu_bits", ptr(dy), ptr(mask), ptr(W), ptr(xin), ptr(xbits),
+                             ptr(dx), ptr(dbp), N, C.byref(s), prec, ptr(ws), ws.numel(), stream_ptr(),
+                             tag="a2c_conv2d_bwd_data|flops|" + sig, work=flops)
+                    else:
+                        call("a2c_conv2d_bwd_data_relu", ptr(dy), ptr(mask), ptr(W), ptr(xin), ptr(dx), ptr(dbp),
+                             N, C.byref(s), prec, ptr(ws), ws.numel(), stream_ptr(),
+                             tag="a2c_conv2d_bwd_data|flops|" + sig, work=flops)
                     grads[2 * (l - 1) + 1] = dbp
                 else:
                     call("a2c_conv2d_bwd_data", ptr(dy), ptr(mask), ptr(W), ptr(dx), N, C.byref(s), prec,

@@ -33,6 +33,8 @@
 
 #include <atomic>
 
+#include <type_traits>
+
 #include "tc_core.cuh"
 
 namespace a2c {
@@ -84,6 +86,12 @@ struct ShiftParams {
   float* out;
   const float* omask;     // optional, same shape as out: out = omask > 0 ? value : 0  (the ReLU of the layer
                           // that produced this layer's input, applied where its gradient is born)
+  // 1-bit ReLU masks, u8 [N, J / 8, OutH * OutW]: bit (c & 7) of byte [n, c >> 3, pos] = out[n, c, pos] > 0.
+  // obits (forward, relu): written next to `out`; omaskbits (MASKOUT): read instead of the fp32 omask
+  // (one byte per 8 channels and position instead of eight strided floats: the masked epilogue of a
+  // stride-2 input gradient spent 2 ms of its 4.2 ms on those loads).
+  uint8_t* obits;
+  const uint8_t* omaskbits;
   double* obias;          // optional f64 [J]: per-channel sums of the (masked) output = bias gradient of that layer
   int OutH, OutW;
   int half_bytes, buf_bytes, w_half_bytes, nbuf;
@@ -150,8 +158,10 @@ __device__ __forceinline__ void store_split(uint8_t* dst, int half_bytes, float 
 
 // FIRST: first-layer variant (<= 4 real channels padded to one k-step, optional uint8 ring source,
 // optional 2-product split); a template flag so the general kernel's hot loops stay branch-free.
-// MASKOUT: backward-data variant whose epilogue applies omask and accumulates obias.
-template <int NPAD, bool FIRST, bool MASKOUT = false>
+// MASKOUT: backward-data variant whose epilogue applies the ReLU mask of the layer below and accumulates
+// obias: 1 = fp32 mask (omask), 2 = 1-bit mask (omaskbits; one register instead of NCOL -- with both forms
+// in one kernel the running bias sums spilled to local memory and the kernel ran 3x slower).
+template <int NPAD, bool FIRST, int MASKOUT = 0>
 __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_constant__ ShiftParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int NCOL = NPAD / 2;                      // accumulator columns per drain warp
@@ -447,7 +457,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const BandInfo bd = band_info(p, item);
       float* oimg = p.out + ((long long)bd.img * p.J + p.n0 + col0) * plane;
-      const float* mimg = MASKOUT ? p.omask + ((long long)bd.img * p.J + p.n0 + col0) * plane : nullptr;
+      const float* mimg = MASKOUT == 1 ? p.omask + ((long long)bd.img * p.J + p.n0 + col0) * plane : nullptr;
       for (int oc = 0; oc < p.noc; ++oc) {
         const ShiftClass c = p.oc[oc];
         int jr = jr0, i = i0;
@@ -458,8 +468,15 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
           const int j = bd.r0 + jr;
           const bool pvalid = jr < bd.rows && j < c.qh && i < c.qw && !(p.dbg & 8);
           const int idx0 = (j * p.os + c.a) * p.OutW + i * p.os + c.b;
-          float mk[MASKOUT ? NCOL : 1];
-          if constexpr (MASKOUT) {
+          float mk[MASKOUT == 1 ? NCOL : 1];
+          uint32_t mbits = 0;
+          if constexpr (MASKOUT == 2) {
+            const uint8_t* bimg = p.omaskbits + ((long long)bd.img * (p.J >> 3) + ((p.n0 + col0) >> 3)) * plane;
+#pragma unroll
+            for (int b8 = 0; b8 < NCOL / 8; ++b8)
+              if (pvalid && b8 * 8 < nvalid) mbits |= (uint32_t)__ldg(bimg + (long long)b8 * plane + idx0) << (8 * b8);
+          }
+          if constexpr (MASKOUT == 1) {
             // the NEXT tile's mask lines go to L2 now (no registers held), so that its loads below hit L2:
             // the drain handles tiles one after the other and would otherwise pay HBM latency per tile
             {
@@ -520,24 +537,40 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[ab]);
           if (pvalid) {
-            int idx = idx0;
+            // WB: also pack the ReLU bits of the stored values (forward layers that leave a 1-bit mask);
+            // a separate instantiation so that the other layers do not pay two instructions per element
+            auto emit = [&](auto wb_tag) {
+              constexpr bool WB = decltype(wb_tag)::value;
+              int idx = idx0;
+              uint32_t rbits = 0;
 #pragma unroll
-            for (int j4 = 0; j4 < NCOL / 4; ++j4) {
-              const float4 b4 = bias4[j4];
-              const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+              for (int j4 = 0; j4 < NCOL / 4; ++j4) {
+                const float4 b4 = bias4[j4];
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                if (j4 * 4 + u < nvalid) {
-                  float v = fmaxf(acc[j4 * 4 + u] + bb[u], floor_v);
-                  if constexpr (MASKOUT) {
-                    v = mk[j4 * 4 + u] > 0.0f ? v : 0.0f;
-                    bsum[j4 * 4 + u] += v;
+                for (int u = 0; u < 4; ++u) {
+                  if (j4 * 4 + u < nvalid) {
+                    float v = fmaxf(acc[j4 * 4 + u] + bb[u], floor_v);
+                    if constexpr (MASKOUT != 0) {
+                      const bool on = MASKOUT == 1 ? mk[MASKOUT == 1 ? j4 * 4 + u : 0] > 0.0f : ((mbits >> (j4 * 4 + u)) & 1u) != 0;
+                      v = on ? v : 0.0f;
+                      bsum[j4 * 4 + u] += v;
+                    }
+                    if constexpr (WB) rbits |= (v > 0.0f ? 1u : 0u) << (j4 * 4 + u);
+                    oimg[idx] = v;
                   }
-                  oimg[idx] = v;
+                  idx += plane;
                 }
-                idx += plane;
               }
-            }
+              if constexpr (WB) {
+                uint8_t* bimg = p.obits + ((long long)bd.img * (p.J >> 3) + ((p.n0 + col0) >> 3)) * plane + idx0;
+#pragma unroll
+                for (int b8 = 0; b8 < NCOL / 8; ++b8)
+                  if (b8 * 8 < nvalid) bimg[(long long)b8 * plane] = (uint8_t)(rbits >> (8 * b8));
+              }
+            };
+            if (MASKOUT == 0 && p.obits) emit(std::true_type{});
+            else emit(std::false_type{});
           }
           jr += q128; i += r128;
           if (i >= p.PW) { i -= p.PW; ++jr; }
@@ -603,7 +636,7 @@ static bool shift_plan(ShiftParams* p, int npad) {
   return false;
 }
 
-template <int NPAD, bool FIRST = false, bool MASKOUT = false>
+template <int NPAD, bool FIRST = false, int MASKOUT = 0>
 static int shift_launch(ShiftParams& p, cudaStream_t st) {
   auto kern = conv_shift_kernel<NPAD, FIRST, MASKOUT>;
   A2C_CUDA_CHECK(set_max_dynamic_smem(reinterpret_cast<const void*>(kern), SH_SMEM_LIMIT));
@@ -635,7 +668,7 @@ static int shift_run(ShiftParams& p, FillTaps fill, cudaStream_t st) {
   for (int ci = 0; ci < 3; ++ci) {
     const int npad = cands[ci];
     if (npad >= 2 * p.J && npad > 16) continue;                 // do not pad a narrow layer to a wide tile
-    if (p.omask && npad == 64) continue;                        // masked epilogue: 16 / 32 wide only
+    if ((p.omask || p.omaskbits) && npad == 64) continue;       // masked epilogue: 16 / 32 wide only
     if (2 * p.nch * 2 * npad > 512) continue;                   // TMEM columns: 2 slots x nch chains x (hi | lo) halves
     if ((long long)p.ntaps_total * p.ksteps * npad * 64 > 80 * 1024 && npad > 16) continue;
     if (!tc::shift_plan(&p, npad)) continue;
@@ -647,9 +680,10 @@ static int shift_run(ShiftParams& p, FillTaps fill, cudaStream_t st) {
       if (p.cvalid < p.C) {
         if (npad == 64) return 1;                                 // first layers: 16 / 32 wide only
         rc = npad == 32 ? tc::shift_launch<32, true>(p, st) : tc::shift_launch<16, true>(p, st);
-      } else if (p.omask) {
+      } else if (p.omask || p.omaskbits) {
         if (npad == 64) return 1;                                 // masked epilogue: up to 32 channels per pass
-        rc = npad == 32 ? tc::shift_launch<32, false, true>(p, st) : tc::shift_launch<16, false, true>(p, st);
+        if (p.omaskbits) rc = npad == 32 ? tc::shift_launch<32, false, 2>(p, st) : tc::shift_launch<16, false, 2>(p, st);
+        else rc = npad == 32 ? tc::shift_launch<32, false, 1>(p, st) : tc::shift_launch<16, false, 1>(p, st);
       } else {
         rc = npad == 64 ? tc::shift_launch<64>(p, st) : npad == 32 ? tc::shift_launch<32>(p, st)
                                                                    : tc::shift_launch<16>(p, st);
@@ -663,7 +697,7 @@ static int shift_run(ShiftParams& p, FillTaps fill, cudaStream_t st) {
 
 // 0 = ran, 1 = not supported (caller falls back), else error
 int conv_fwd_shift_try(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias, float* Y,
-                       int N, const a2c_conv_shape* s, int relu, cudaStream_t st) {
+                       int N, const a2c_conv_shape* s, int relu, cudaStream_t st, uint8_t* relu_bits) {
   const int K = s->K, S = s->stride, P = s->pad;
   // first layers (<= 4 channels, stride 1): channels padded to one 8-deep k-step; the source may be
   // the uint8 plane ring, whose {0,1} values are exact in TF32 (no lo operand)
@@ -696,6 +730,8 @@ int conv_fwd_shift_try(const float* X, const a2c_state_view* xview, const float*
   p.ntaps_total = K * K; p.nch = K;                 // one accumulator chain per kernel row
   p.wt = Wt; p.wsn = s->Cin * K * K; p.wsk = K * K; p.J = s->Cout; p.bias = bias; p.relu = relu;
   p.out = Y; p.OutH = s->OH; p.OutW = s->OW;
+  if (relu_bits && (!relu || (s->Cout & 7))) return 1;
+  p.obits = relu_bits;
   return shift_run(p, [K, S](ShiftParams& q) {
     for (int ky = 0; ky < K; ++ky)
       for (int kx = 0; kx < K; ++kx) {
@@ -717,10 +753,12 @@ bool conv_dgrad_shift_ok(const a2c_conv_shape* s) {
 // Xmask / dbias_prev (both optional): dX = Xmask > 0 ? dX : 0 and dbias_prev f64 [Cin] += per-channel sums
 // of the masked dX (the caller zeroes it) -- the ReLU + bias gradient of the layer that produced X.
 int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, float* dX, const float* Xmask,
-                         double* dbias_prev, int N, const a2c_conv_shape* s, cudaStream_t st) {
+                         double* dbias_prev, int N, const a2c_conv_shape* s, cudaStream_t st,
+                         const uint8_t* Xbits) {
   const int K = s->K, S = s->stride, P = s->pad;
   if (!conv_dgrad_shift_ok(s)) return 1;
-  if (dbias_prev && !Xmask) return 1;
+  if (dbias_prev && !Xmask && !Xbits) return 1;
+  if (Xbits && (s->Cin & 7)) Xbits = nullptr;          // (the fp32 mask is always passed as well)
   static thread_local ShiftParams p;
   memset(&p, 0, sizeof(p));
   p.src = dY; p.mask = Ymask; p.N = N; p.C = s->Cout; p.SH = s->OH; p.SW = s->OW;
@@ -748,7 +786,7 @@ int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, f
   p.nch = 1;
   p.wt = Wt; p.wsn = K * K; p.wsk = s->Cin * K * K; p.J = s->Cin;
   p.out = dX; p.OutH = s->H; p.OutW = s->W;
-  p.omask = Xmask; p.obias = dbias_prev;
+  p.omask = Xbits ? nullptr : Xmask; p.omaskbits = Xbits; p.obias = dbias_prev;
   p.ntaps_total = K * K;
   const int H = s->H, W = s->W;
   return shift_run(p, [K, S, P, H, W, dmin](ShiftParams& q) {

@@ -478,9 +478,27 @@ int conv_wgrad_tc_try(const float* X, const a2c_state_view* xview, const float* 
 
 // conv_shift_tc.cu (3xTF32 only): 3x3 pad-1 layers as shifted-descriptor GEMMs, no im2col
 int conv_fwd_shift_try(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias, float* Y,
-                       int N, const a2c_conv_shape* s, int relu, cudaStream_t st);
+                       int N, const a2c_conv_shape* s, int relu, cudaStream_t st, uint8_t* relu_bits = nullptr);
 int conv_dgrad_shift_try(const float* dY, const float* Ymask, const float* Wt, float* dX, const float* Xmask,
-                         double* dbias_prev, int N, const a2c_conv_shape* s, cudaStream_t st);
+                         double* dbias_prev, int N, const a2c_conv_shape* s, cudaStream_t st,
+                         const uint8_t* Xbits = nullptr);
+
+// bits u8 [N, C / 8, HW]: bit (c & 7) of byte [n, c >> 3, pos] = Y[n, c, pos] > 0  (fallback producer of the
+// 1-bit ReLU masks for forward paths that do not write them in their epilogue)
+__global__ void __launch_bounds__(256)
+relu_bits_kernel(const float* __restrict__ Y, uint8_t* __restrict__ bits, long long nbytes, int C, int HW) {
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nbytes; i += (long long)gridDim.x * 256) {
+    const int pos = (int)(i % HW);
+    const long long nc8 = i / HW;
+    const int c8 = (int)(nc8 % (C >> 3));
+    const long long n = nc8 / (C >> 3);
+    const float* y = Y + (n * C + c8 * 8) * HW + pos;
+    uint32_t b = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) b |= (__ldg(y + (long long)u * HW) > 0.0f ? 1u : 0u) << u;
+    bits[i] = (uint8_t)b;
+  }
+}
 
 // acc f64 [C] += per-channel sums of X f32 [N, C, HW] (where mask > 0, mask optional)
 __global__ void __launch_bounds__(256)
@@ -586,6 +604,28 @@ int a2c_conv2d_fwd(const float* X, const a2c_state_view* xview, const float* Wt,
   return launch_fwd(p, s->K, s->stride, s->W, as_stream(stream));
 }
 
+int a2c_conv2d_fwd_relu_bits(const float* X, const a2c_state_view* xview, const float* Wt, const float* bias,
+                             float* Y, unsigned char* relu_bits, int N, const a2c_conv_shape* s, int precision,
+                             void* stream) {
+  if (int rc = check_shape(s)) return rc;
+  A2C_ARG_CHECK(Wt && Y && relu_bits && N >= 0 && (xview || X), "conv_fwd_relu_bits: bad args");
+  A2C_ARG_CHECK((s->Cout & 7) == 0, "conv_fwd_relu_bits: Cout must be a multiple of 8");
+  if (N == 0) return 0;
+  if (precision == 1) {
+    // the shift-GEMM epilogue writes the bits next to Y
+    A2C_PATH_RETURN(0, conv_fwd_shift_try(X, xview, Wt, bias, Y, N, s, 1, as_stream(stream), relu_bits));
+  }
+  // any other path: plain forward, then one pass over Y
+  if (int rc = a2c_conv2d_fwd(X, xview, Wt, bias, Y, N, s, 1, precision, stream)) return rc;
+  const long long nbytes = (long long)N * (s->Cout >> 3) * s->OH * s->OW;
+  long long blocks = cdivll(nbytes, 256);
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  relu_bits_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(Y, relu_bits, nbytes, s->Cout, s->OH * s->OW);
+  g_launches++;
+  A2C_LAUNCH_CHECK();
+  return 0;
+}
+
 int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, float* dX, int N,
                         const a2c_conv_shape* s, int precision, void* stream) {
   if (int rc = check_shape(s)) return rc;
@@ -612,9 +652,31 @@ int a2c_conv2d_bwd_data(const float* dY, const float* Ymask, const float* Wt, fl
   return launch_fwd(p, s->K, 1, logicalW, as_stream(stream));
 }
 
+static int bwd_data_relu_impl(const float* dY, const float* Ymask, const float* Wt, const float* X,
+                              const unsigned char* Xbits, float* dX, float* dbias_prev, int N,
+                              const a2c_conv_shape* s, int precision, void* workspace, long long workspace_bytes,
+                              void* stream);
+
 int a2c_conv2d_bwd_data_relu(const float* dY, const float* Ymask, const float* Wt, const float* X, float* dX,
                              float* dbias_prev, int N, const a2c_conv_shape* s, int precision, void* workspace,
                              long long workspace_bytes, void* stream) {
+  return bwd_data_relu_impl(dY, Ymask, Wt, X, nullptr, dX, dbias_prev, N, s, precision, workspace, workspace_bytes,
+                            stream);
+}
+
+int a2c_conv2d_bwd_data_relu_bits(const float* dY, const float* Ymask, const float* Wt, const float* X,
+                                  const unsigned char* Xbits, float* dX, float* dbias_prev, int N,
+                                  const a2c_conv_shape* s, int precision, void* workspace,
+                                  long long workspace_bytes, void* stream) {
+  A2C_ARG_CHECK(Xbits, "conv_bwd_data_relu_bits: null Xbits");
+  return bwd_data_relu_impl(dY, Ymask, Wt, X, Xbits, dX, dbias_prev, N, s, precision, workspace, workspace_bytes,
+                            stream);
+}
+
+static int bwd_data_relu_impl(const float* dY, const float* Ymask, const float* Wt, const float* X,
+                              const unsigned char* Xbits, float* dX, float* dbias_prev, int N,
+                              const a2c_conv_shape* s, int precision, void* workspace, long long workspace_bytes,
+                              void* stream) {
   if (int rc = check_shape(s)) return rc;
   A2C_ARG_CHECK(dY && Wt && X && dX && N >= 0, "conv_bwd_data_relu: bad args");
   A2C_ARG_CHECK(!dbias_prev || (workspace && workspace_bytes >= (long long)sizeof(double) * s->Cin),
@@ -624,7 +686,7 @@ int a2c_conv2d_bwd_data_relu(const float* dY, const float* Ymask, const float* W
   if (acc) A2C_CUDA_CHECK(cudaMemsetAsync(acc, 0, sizeof(double) * s->Cin, st));
   if (N > 0) {
     int rc = 1;
-    if (precision == 1) rc = conv_dgrad_shift_try(dY, Ymask, Wt, dX, X, acc, N, s, st);
+    if (precision == 1) rc = conv_dgrad_shift_try(dY, Ymask, Wt, dX, X, acc, N, s, st, Xbits);
     if (rc != 0 && rc != 1) return rc;
     if (rc == 0) g_last_path = 0;
     if (rc == 1) {

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared_symbols():
         assert hasattr(lib, name), "missing export: " + name
-    assert lib.a2c_abi_version() == 2
+    assert lib.a2c_abi_version() == 3
     # the ctypes table binds exactly the declared entry points
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     _lib.load()

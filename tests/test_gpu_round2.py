@@ -444,6 +444,51 @@ def test_conv_stack_mask_at_source(dev, stack, precision, tol):
         ops.set_precision(old)
 
 
+@pytest.mark.parametrize("precision", [1, 0])
+@pytest.mark.parametrize("Cin,Cout,Cnext,Hh,S", [(16, 24, 32, 80, 2), (32, 48, 64, 20, 2), (8, 16, 24, 40, 1)])
+def test_relu_bits_entries(dev, precision, Cin, Cout, Cnext, Hh, S):
+    """1-bit ReLU masks: a2c_conv2d_fwd_relu_bits writes bit (c & 7) of byte [n, c >> 3, pos] = Y > 0 next to
+    the same Y as a2c_conv2d_fwd, and a2c_conv2d_bwd_data_relu_bits gives bit-identical results to
+    a2c_conv2d_bwd_data_relu reading the fp32 activations (shift-GEMM epilogues at precision 1, the
+    fallback passes at precision 0)."""
+    import ctypes as C
+    from a2c_b200 import ops
+    from a2c_b200._lib import call, ptr, stream_ptr
+    g = torch.Generator().manual_seed(11)
+    N = 6
+    x = torch.randn(N, Cin, Hh, Hh, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / np.sqrt(Cin * 9.0)).to(dev)
+    b = (torch.randn(Cout, generator=g) * 0.1).to(dev)
+    s = ops.conv_shape(Cin, Cout, Hh, Hh, 3, 1, 1)
+    y0 = torch.empty(N, Cout, s.OH, s.OW, device=dev); y1 = torch.empty_like(y0)
+    bits = torch.zeros(N, Cout // 8, s.OH * s.OW, dtype=torch.uint8, device=dev)
+    call("a2c_conv2d_fwd", ptr(x), None, ptr(w), ptr(b), ptr(y0), N, C.byref(s), 1, precision, stream_ptr())
+    call("a2c_conv2d_fwd_relu_bits", ptr(x), None, ptr(w), ptr(b), ptr(y1), ptr(bits), N, C.byref(s), precision,
+         stream_ptr())
+    assert torch.equal(y0, y1)
+    want = (y0 > 0).reshape(N, Cout // 8, 8, s.OH * s.OW).to(torch.int32)
+    want = (want * (2 ** torch.arange(8, device=dev, dtype=torch.int32)).view(1, 1, 8, 1)).sum(2).to(torch.uint8)
+    assert torch.equal(bits, want)
+    # the layer above: masked input gradient + the bias gradient of this layer, from floats and from bits
+    s2 = ops.conv_shape(Cout, Cnext, s.OH, s.OW, 3, S, 1)
+    w2 = (torch.randn(Cnext, Cout, 3, 3, generator=g) / np.sqrt(Cout * 9.0)).to(dev)
+    dy = torch.randn(N, Cnext, s2.OH, s2.OW, generator=g).to(dev)
+    ws = ops.workspace(dev)
+    outs = []
+    for use_bits in (False, True):
+        dx = torch.full_like(y0, float("nan")); dbp = torch.empty(Cout, device=dev)
+        if use_bits:
+            call("a2c_conv2d_bwd_data_relu_bits", ptr(dy), None, ptr(w2), ptr(y0), ptr(bits), ptr(dx), ptr(dbp), N,
+                 C.byref(s2), precision, ptr(ws), ws.numel(), stream_ptr())
+        else:
+            call("a2c_conv2d_bwd_data_relu", ptr(dy), None, ptr(w2), ptr(y0), ptr(dx), ptr(dbp), N, C.byref(s2),
+                 precision, ptr(ws), ws.numel(), stream_ptr())
+        outs.append((dx, dbp))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert H.rel_err(outs[1][1].cpu().numpy(), outs[0][1].cpu().numpy()) < 1e-6      # (f64 atomics: order)
+    assert bool(((outs[1][0] != 0) <= (y0 > 0)).all())
+
+
 def test_conv_stack_unmasked_gradient_and_tensor_input(dev):
     """premasked=False (the caller hands an unmasked output gradient) and a float tensor input
     that itself needs a gradient."""
