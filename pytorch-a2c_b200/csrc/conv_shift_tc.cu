@@ -539,9 +539,14 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
           if (pvalid) {
             // WB: also pack the ReLU bits of the stored values (forward layers that leave a 1-bit mask);
             // a separate instantiation so that the other layers do not pay two instructions per element
-            auto emit = [&](auto wb_tag) {
+            // FULL: all NCOL channels of this warp exist (no per-element bound check); the output pointer
+            // advances by one plane per channel (the drain is a critical role of these kernels: 64-bit
+            // index arithmetic and a compare + branch per element were 2/3 of its instructions)
+            auto emit = [&](auto wb_tag, auto full_tag) {
               constexpr bool WB = decltype(wb_tag)::value;
-              int idx = idx0;
+              constexpr bool FULL = decltype(full_tag)::value;
+              float* optr = oimg + idx0;           // MASKOUT == 0
+              int idx = idx0;                      // MASKOUT != 0 (one register less: those variants are at the limit)
               uint32_t rbits = 0;
 #pragma unroll
               for (int j4 = 0; j4 < NCOL / 4; ++j4) {
@@ -549,7 +554,7 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
                 const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  if (j4 * 4 + u < nvalid) {
+                  if (FULL || j4 * 4 + u < nvalid) {
                     float v = fmaxf(acc[j4 * 4 + u] + bb[u], floor_v);
                     if constexpr (MASKOUT != 0) {
                       const bool on = MASKOUT == 1 ? mk[MASKOUT == 1 ? j4 * 4 + u : 0] > 0.0f : ((mbits >> (j4 * 4 + u)) & 1u) != 0;
@@ -557,9 +562,9 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
                       bsum[j4 * 4 + u] += v;
                     }
                     if constexpr (WB) rbits |= (v > 0.0f ? 1u : 0u) << (j4 * 4 + u);
-                    oimg[idx] = v;
+                    if constexpr (MASKOUT == 0) *optr = v; else oimg[idx] = v;
                   }
-                  idx += plane;
+                  if constexpr (MASKOUT == 0) optr += plane; else idx += plane;
                 }
               }
               if constexpr (WB) {
@@ -569,8 +574,15 @@ __global__ void __launch_bounds__(SH_THREADS, 1) conv_shift_kernel(const __grid_
                   if (b8 * 8 < nvalid) bimg[(long long)b8 * plane] = (uint8_t)(rbits >> (8 * b8));
               }
             };
-            if (MASKOUT == 0 && p.obits) emit(std::true_type{});
-            else emit(std::false_type{});
+            if constexpr (MASKOUT != 0) {
+              emit(std::false_type{}, std::false_type{});      // (more variants spill the running bias sums)
+            } else if (nvalid == NCOL) {
+              if (p.obits) emit(std::true_type{}, std::true_type{});
+              else emit(std::false_type{}, std::true_type{});
+            } else {
+              if (p.obits) emit(std::true_type{}, std::false_type{});
+              else emit(std::false_type{}, std::false_type{});
+            }
           }
           jr += q128; i += r128;
           if (i >= p.PW) { i -= p.PW; ++jr; }
