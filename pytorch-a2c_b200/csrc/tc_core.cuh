@@ -179,7 +179,7 @@ __device__ __forceinline__ void store_elem(uint8_t* hi_tile, uint8_t* lo_tile, i
 // t = thread index within the operand's producer warps.
 template <int BN, bool SPLIT3, class P>
 __global__ void __launch_bounds__(32 * (P::NA + P::NB + NUM_EPI_WARPS + 1), 1)
-tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
+tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles, int group_m) {
   constexpr int NUM_PROD_WARPS = P::NA + P::NB;
   constexpr int KC = P::KC;
   constexpr int EPI0 = NUM_PROD_WARPS, MMA_WARP = EPI0 + NUM_EPI_WARPS, ALLOC_WARP = MMA_WARP;   // the MMA warp owns TMEM
@@ -208,10 +208,10 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles) {
   const int total_tiles = mtiles * ntiles;
   const int tile0 = blockIdx.x, tile_step = gridDim.x;
   auto tile_of = [&](int t, int& mt, int& nt) {
-    const int per_group = TILE_GROUP_M * ntiles;
+    const int per_group = group_m * ntiles;
     const int g = t / per_group, r = t - g * per_group;
-    const int first_m = g * TILE_GROUP_M;
-    const int gsize = min(TILE_GROUP_M, mtiles - first_m);
+    const int first_m = g * group_m;
+    const int gsize = min(group_m, mtiles - first_m);
     nt = r / gsize;
     mt = first_m + (r - nt * gsize);
   };
@@ -506,7 +506,9 @@ int tc_launch(const typename P::Params& p, int mtiles, int ntiles, int splits, c
   if (ncta < 1) ncta = 1;
   if (ncta > mtiles * ntiles) ncta = mtiles * ntiles;
   dim3 grid(ncta, 1, splits);
-  kern<<<grid, 32 * (P::NA + P::NB + NUM_EPI_WARPS + 1), smem, st>>>(p, stages, mtiles, ntiles);
+  int group_m = TILE_GROUP_M;
+  if (const int k = debug_knob("A2C_TC_GROUP")) group_m = k;
+  kern<<<grid, 32 * (P::NA + P::NB + NUM_EPI_WARPS + 1), smem, st>>>(p, stages, mtiles, ntiles, group_m);
   return 0;
 }
 
