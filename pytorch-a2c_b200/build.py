@@ -2,6 +2,10 @@
 library is a plain C-ABI shared object (include/a2c_b200.h).
 
     python pytorch-a2c_b200/build.py [--force]
+
+Profiling builds (never the shipped library): A2C_NVCC_FLAGS="-DA2C_DEBUG_KNOBS" enables the stage-isolation
+environment knobs, A2C_NVCC_FLAGS="-DA2C_TC_TRACE" the per-role clock stamps of the tcgen05 GEMM and the
+weight-gradient kernel (a2c_debug_tc_trace / a2c_debug_wg_trace, DESIGN.md lessons 19 and 22).
 """
 import concurrent.futures
 import hashlib
