@@ -80,3 +80,20 @@ def test_fused_mask_query_is_host_logic():
     assert q(shape(48, 64, 10, 3, 2, 1), 1) == 7            # GRUModel's 10x10 layer: scalar producers, 32 + 16 channel chunks
     assert q(shape(16, 32, 19, 4, 2, 0), 1) == 0            # A3C's 4x4 s2 layer: pre-masked gradient
     assert q(shape(16, 24, 80, 3, 1, 1), 2) == 0            # single-pass TF32 paths want the masked dY
+
+
+def test_relu_bits_entries_check_their_arguments():
+    """The 1-bit ReLU mask entries reject a null bit plane and channel counts that are not multiples
+    of 8 before touching the device (host-side checks: runs without a GPU)."""
+    from a2c_b200 import _lib
+    lib = _lib.load()
+    sh = _lib.ConvShape(16, 12, 8, 8, 8, 8, 3, 1, 1)
+    buf = (ctypes.c_float * 4)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    rc = lib.a2c_conv2d_fwd_relu_bits(p, None, p, p, p, p, 1, ctypes.byref(sh), 1, None)
+    assert rc == -1 and b"multiple of 8" in lib.a2c_last_error()
+    sh = _lib.ConvShape(16, 16, 8, 8, 8, 8, 3, 1, 1)
+    rc = lib.a2c_conv2d_fwd_relu_bits(p, None, p, p, p, None, 1, ctypes.byref(sh), 1, None)
+    assert rc == -1
+    rc = lib.a2c_conv2d_bwd_data_relu_bits(p, None, p, p, None, p, None, 1, ctypes.byref(sh), 1, None, 0, None)
+    assert rc == -1 and b"Xbits" in lib.a2c_last_error()
