@@ -2,22 +2,22 @@
 //
 // One CTA computes a 128 x BN fp32 tile  D = sum_k A[m,k] * B[n,k]  on the 5th-gen
 // tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM):
-//   NA warps    producers of the A tile   (Problem::produce_a)
-//   NB warps    producers of the B tile   (Problem::produce_b)
+//   NA warps    producers of the A tile   (Problem::load_a / store_a)
+//   NB warps    producers of the B tile   (Problem::load_b / store_b)
 //   8 warps     accumulator drain + epilogue (Problem::epilogue)
-//   1 warp      MMA issuer (one elected lane);  1 warp TMEM allocator
+//   1 warp      MMA issuer (one elected lane), which also owns the TMEM allocation
 // Operand tiles live in shared memory in the canonical K-major SWIZZLE_128B UMMA
 // layout: rows of 32 fp32 (128 B), 16-byte chunk index XOR (row & 7), 8-row
 // groups 1024 B apart.  Producers are ordinary threads, so a Problem can gather
 // (im2col, transposed, masked, u8 -> f32) while it fills the tile -- no operand
 // is ever materialised in HBM in a tensor-core friendly layout.
 //
-// SPLIT3 (3xTF32): hi = rna_tf32(x), lo = x - hi;  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, issued as
+// SPLIT3 (3xTF32): hi = tf32(x), lo = tf32(x - hi) (round to nearest, one F2FP each);  D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, issued as
 // TWO instructions per k-step:  D[:, 0:2BN] (+)= A_hi * [B_hi | B_lo]  (the lo tile follows the hi tile in
 // shared memory, so one descriptor of width 2 BN covers both) and  D[:, 0:BN] += A_lo * B_hi;  the drain
 // adds the two column halves.  Same tensor-pipe work as three MMAs, but the A tile is fetched from
-// shared memory twice instead of three times -- and this kernel is bound by shared-memory bandwidth
-// (operand stores of the producers + operand fetches of the tensor core), not by the tensor pipe.
+// shared memory twice instead of three times.  (What bounds the kernel is the serial loop of the producer
+// warps and the L2 -> SM latency their two fragments in flight have to cover: DESIGN.md lessons 18-19.)
 // The TMEM accumulator adds with truncation (measured on B200: error grows
 // linearly with the number of chained MMAs, 2e-4 at K = 25600), so K is consumed
 // in chunks of KC k-blocks into two ping-pong TMEM accumulators and the drain
@@ -246,9 +246,9 @@ tc_kernel(const typename P::Params p, int stages, int mtiles, int ntiles, int gr
   auto stage_ptr = [&](int s) { return smem + s * STAGE_BYTES; };
   // stage layout: [A_hi][A_lo?][B_hi][B_lo?]
   if (warp < P::NA) {
-    // ---- A producers.  The global loads run P::DEPTH k-blocks ahead of the convert-and-store
-    // step: the producers are latency-bound (bytes in flight = registers holding loads), so the
-    // GEMM uses 16 producer warps with two k-blocks in flight each.
+    // ---- A producers.  P::DEPTH + 1 fragments per thread: while one is converted and stored, the
+    // loads of the next P::DEPTH k-blocks are in flight (the L2 -> SM latency is ~1,500 clk under this
+    // load, about one and a half k-block periods); the GEMM uses 16 producer warps.
     const int t = threadIdx.x;
     StageRing ring(stages);
     if (tile0 < total_tiles && nkb > 0) {
